@@ -1,0 +1,115 @@
+// common.cuh -- shared device/host plumbing of librspcl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/rspcl.h"
+
+struct rspcl_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long long launches = 0;
+  std::string err;
+  int sm_count = 148;
+  // grow-only pinned staging buffer for small result read-backs
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+};
+
+struct rspcl_cloud {
+  float4* pts = nullptr;   // [n_seg * stride] {x,y,z,rgba bits}
+  int* count = nullptr;    // [n_seg] device-resident point counts
+  uint8_t* gray = nullptr; // organized clouds: (r+g+b)/3 plane written by the upload kernel, [n_seg * stride]
+  int n_seg = 0;
+  int stride = 0;
+  int width = 0, height = 0;  // organized when height > 0
+  int max_count_hint = 0;     // host-side upper bound of any segment count (stride if unknown)
+};
+
+#define RSPCL_FAIL(ctx, code, ...)                    \
+  do {                                                \
+    char _b[512];                                     \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);            \
+    (ctx)->err = _b;                                  \
+    return (code);                                    \
+  } while (0)
+
+#define CU(ctx, call)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      char _b[512];                                                                               \
+      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      (ctx)->err = _b;                                                                            \
+      return RSPCL_ERR_CUDA;                                                                      \
+    }                                                                                             \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)            \
+  do {                               \
+    (ctx)->launches++;               \
+    CU(ctx, cudaGetLastError());     \
+  } while (0)
+
+// stream-ordered scratch (cudaMallocAsync pool: no synchronisation after warm-up)
+template <typename T>
+static inline cudaError_t scratch_alloc(rspcl_ctx* ctx, T** p, size_t n) {
+  return cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), ctx->stream);
+}
+template <typename T>
+static inline void scratch_free(rspcl_ctx* ctx, T* p) {
+  if (p) cudaFreeAsync((void*)p, ctx->stream);
+}
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int ensure_stage(rspcl_ctx* ctx, size_t bytes);
+int blocks_per_seg(const rspcl_ctx* ctx, int n_seg, int max_count, int threads);
+int transform_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float* d_T, int broadcast, rspcl_cloud* out);
+int ensure_gray(rspcl_ctx* ctx, rspcl_cloud* c);
+
+// ---- exclusive scan of int32 on the context stream (scan.cu) ----
+int rspcl_exclusive_scan_i32(rspcl_ctx* ctx, const int* in, int* out, long long n, int* total_out /* device, may be null */);
+
+// ---- float helpers that must round exactly like the oracle (no FMA contraction) ----
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+
+// x' = ((m00*x + m01*y) + m02*z) + m03, column-major M (pcl/common/impl/transforms.hpp)
+__device__ __forceinline__ float3 xform_point(const float* __restrict__ M, float x, float y, float z) {
+  float3 o;
+  o.x = fadd(fadd(fadd(fmul(M[0], x), fmul(M[4], y)), fmul(M[8], z)), M[12]);
+  o.y = fadd(fadd(fadd(fmul(M[1], x), fmul(M[5], y)), fmul(M[9], z)), M[13]);
+  o.z = fadd(fadd(fadd(fmul(M[2], x), fmul(M[6], y)), fmul(M[10], z)), M[14]);
+  return o;
+}
+
+__device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
+
+// static_cast<int>(floor(v)) with x86-64 cvttss2si semantics (NaN / overflow -> INT_MIN)
+__device__ __forceinline__ int floor_to_int_x86(float v) {
+  float f = floorf(v);
+  if (!(f >= -2147483648.0f && f < 2147483648.0f)) return (int)0x80000000;
+  return (int)f;
+}
+
+// FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz
+__device__ __forceinline__ float dist2_l2simple(float ax, float ay, float az, float bx, float by, float bz) {
+  float d = __fsub_rn(ax, bx);
+  float r = fmul(d, d);
+  d = __fsub_rn(ay, by);
+  r = fadd(r, fmul(d, d));
+  d = __fsub_rn(az, bz);
+  r = fadd(r, fmul(d, d));
+  return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}

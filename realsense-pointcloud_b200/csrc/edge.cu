@@ -1,0 +1,363 @@
+// edge.cu -- RGB-Canny edge extraction of organized clouds and ordered compaction into edge clouds.
+//
+// Replaces /root/reference/src/edge_extractor.hpp:7-39 (extract_edge_features).  Only label_indices[4]
+// (EDGELABEL_RGB_CANNY) reaches the caller (edge_extractor.hpp:36-38) and it depends on rgb alone, so the
+// integral-image normals and the four depth/curvature edge classes the reference computes and discards
+// (edge_extractor.hpp:10-15,26-35) are not computed here.
+//
+// Kernels (all bit-exact against oracle/orc_edge.cpp; mul/add are explicitly un-fused):
+//   K1  k_canny_nms   gray -> 3x3 Gaussian (9-tap, clamp) -> Sobel (clamp) -> sqrtf magnitude -> direction bin
+//                     -> non-maximum suppression, fused over a shared-memory halo tile; writes a 1-byte class
+//                     (0 none, 1 weak >= t_low, 2 strong >= t_high) and seeds the union-find parents.
+//   K1b k_uf_merge / k_uf_flag / k_edge_mask   hysteresis as 8-connected components of {class>0} that contain a
+//                     strong pixel (lock-free union-find; the result is order-independent, so it is exact).
+//   K1c k_block_count / k_seg_scan / k_scatter  mask -> ascending row-major compaction (copyPointCloud(indices)).
+// Roofline: HBM-bound; algorithmic bytes per pixel = 1 R (gray) + 1 W (class) for K1.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TW = 64, TH = 16;          // output tile
+constexpr int GW = TW + 6, GH = TH + 6;  // gray tile (halo 3)
+constexpr int BW = TW + 4, BH = TH + 4;  // blur tile (halo 2)
+constexpr int MW = TW + 2, MH = TH + 2;  // magnitude tile (halo 1)
+
+// pcl/2d/impl/kernel.hpp gaussianKernel(3, sigma=1) in float (checked by tests/test_oracle.py)
+__constant__ float c_gauss[9] = {0.07511360943317413f, 0.12384141236543655f, 0.07511360943317413f,
+                                 0.12384141236543655f, 0.20417995750904083f, 0.12384141236543655f,
+                                 0.07511360943317413f, 0.12384141236543655f, 0.07511360943317413f};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// discretizeAngles on atan2f(gy,gx) * 57.29578f.  The angle is evaluated in double and rounded to float, which
+// reproduces a correctly rounded atan2f except within ~1e-9 relative of a rounding boundary; the oracle counts pixels
+// whose angle sits within 1e-3 degrees of a bin threshold (near_bin_edge) so a disagreement would be visible.
+__device__ __forceinline__ int direction_bin(float gy, float gx) {
+  float rad = (float)atan2((double)gy, (double)gx);
+  float angle = fmul(rad, 57.29578f);
+  if (((angle <= 22.5f) && (angle >= -22.5f)) || (angle >= 157.5f) || (angle <= -157.5f)) return 0;
+  if (((angle > 22.5f) && (angle < 67.5f)) || ((angle < -112.5f) && (angle > -157.5f))) return 45;
+  if (((angle >= 67.5f) && (angle <= 112.5f)) || ((angle <= -67.5f) && (angle >= -112.5f))) return 90;
+  if (((angle > 112.5f) && (angle < 157.5f)) || ((angle < -22.5f) && (angle > -67.5f))) return 135;
+  return 255;
+}
+
+__global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ gray, int w, int h, int stride, float t_low,
+                                                   float t_high, uint8_t* __restrict__ cls, int* __restrict__ parent) {
+  __shared__ float s_gray[GH][GW + 1];
+  __shared__ float s_blur[BH][BW + 1];
+  __shared__ float s_mag[MH][MW + 1];
+  const int seg = blockIdx.z;
+  const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const uint8_t* g = gray + (size_t)seg * stride;
+
+  // 1. gray tile with replicate borders (Convolution BOUNDARY_OPTION_CLAMP)
+  for (int k = tid; k < GH * GW; k += 256) {
+    int i = k / GW, j = k % GW;
+    int r = clampi(r0 - 3 + i, 0, h - 1), c = clampi(c0 - 3 + j, 0, w - 1);
+    s_gray[i][j] = (float)g[(size_t)r * w + c];
+  }
+  __syncthreads();
+  // 2. blur evaluated AT THE CLAMPED COORDINATE of every halo-2 position (what the Sobel pass will read)
+  for (int k = tid; k < BH * BW; k += 256) {
+    int i = k / BW, j = k % BW;
+    int r = clampi(r0 - 2 + i, 0, h - 1), c = clampi(c0 - 2 + j, 0, w - 1);
+    int gi = r - (r0 - 3), gj = c - (c0 - 3);
+    float acc = 0.f;
+#pragma unroll
+    for (int kr = 0; kr < 3; ++kr)
+#pragma unroll
+      for (int kc = 0; kc < 3; ++kc) {
+        // in-image neighbour clamp is already baked into s_gray as long as (r,c) itself is in the image
+        acc = fadd(acc, fmul(c_gauss[kr * 3 + kc], s_gray[gi + kr - 1][gj + kc - 1]));
+      }
+    s_blur[i][j] = acc;
+  }
+  __syncthreads();
+  // 3. Sobel + magnitude on the halo-1 region (only in-image positions are ever consumed)
+  for (int k = tid; k < MH * MW; k += 256) {
+    int i = k / MW, j = k % MW;
+    int r = r0 - 1 + i, c = c0 - 1 + j;
+    float m = 0.f;
+    if (r >= 0 && r < h && c >= 0 && c < w) {
+      // blur(clamp(r+dr), clamp(c+dc)) lives at tile index (clamped coordinate - (origin-2))
+      int bi[3], bj[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        bi[d] = clampi(r + d - 1, 0, h - 1) - (r0 - 2);
+        bj[d] = clampi(c + d - 1, 0, w - 1) - (c0 - 2);
+      }
+      const float sx[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};
+      const float sy[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};
+      float gx = 0.f, gy = 0.f;
+#pragma unroll
+      for (int kr = 0; kr < 3; ++kr)
+#pragma unroll
+        for (int kc = 0; kc < 3; ++kc) {
+          float v = s_blur[bi[kr]][bj[kc]];
+          gx = fadd(gx, fmul(sx[kr * 3 + kc], v));
+          gy = fadd(gy, fmul(sy[kr * 3 + kc], v));
+        }
+      m = __fsqrt_rn(fadd(fmul(gx, gx), fmul(gy, gy)));
+    }
+    s_mag[i][j] = m;
+  }
+  __syncthreads();
+  // 4. direction + non-maximum suppression for the TH x TW centre (suppressNonMaxima: interior pixels only)
+  for (int k = tid; k < TH * TW; k += 256) {
+    int i = k / TW, j = k % TW;
+    int r = r0 + i, c = c0 + j;
+    if (r >= h || c >= w) continue;
+    uint8_t out = 0;
+    if (r >= 1 && r < h - 1 && c >= 1 && c < w - 1) {
+      float m = s_mag[i + 1][j + 1];
+      if (!(m < t_low)) {
+        // recompute the gradient of this pixel for its direction (cheaper than a second smem plane)
+        int bi[3], bj[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          bi[d] = (r + d - 1) - (r0 - 2);
+          bj[d] = (c + d - 1) - (c0 - 2);
+        }
+        const float sx[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};
+        const float sy[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};
+        float gx = 0.f, gy = 0.f;
+#pragma unroll
+        for (int kr = 0; kr < 3; ++kr)
+#pragma unroll
+          for (int kc = 0; kc < 3; ++kc) {
+            float v = s_blur[bi[kr]][bj[kc]];
+            gx = fadd(gx, fmul(sx[kr * 3 + kc], v));
+            gy = fadd(gy, fmul(sy[kr * 3 + kc], v));
+          }
+        int dir = direction_bin(gy, gx);
+        float a = 0.f, b = 0.f;
+        bool ok = true;
+        switch (dir) {
+          case 0: a = s_mag[i + 1][j]; b = s_mag[i + 1][j + 2]; break;      // (col-1,row) (col+1,row)
+          case 45: a = s_mag[i][j]; b = s_mag[i + 2][j + 2]; break;         // (col-1,row-1) (col+1,row+1)
+          case 90: a = s_mag[i][j + 1]; b = s_mag[i + 2][j + 1]; break;     // (col,row-1) (col,row+1)
+          case 135: a = s_mag[i][j + 2]; b = s_mag[i + 2][j]; break;        // (col+1,row-1) (col-1,row+1)
+          default: ok = false; break;
+        }
+        if (ok && m >= a && m >= b) out = (m >= t_high) ? 2 : 1;
+      }
+    }
+    const size_t gidx = (size_t)seg * stride + (size_t)r * w + c;
+    cls[gidx] = out;
+    if (out) parent[gidx] = r * w + c;
+  }
+}
+
+// ---- lock-free union-find over candidate pixels (per frame; parents are pixel indices within the frame)
+__device__ __forceinline__ int uf_find(volatile int* parent, int x) {
+  int p = parent[x];
+  while (p != x) {
+    int gp = parent[p];
+    if (gp != p) parent[x] = gp;  // path halving: gp is an ancestor, benign under concurrency
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      int t = a;
+      a = b;
+      b = t;
+    }
+    int old = atomicCAS(&parent[a], a, b);  // link the larger root under the smaller
+    if (old == a) return;
+  }
+}
+
+__global__ void k_uf_merge(const uint8_t* __restrict__ cls, int* __restrict__ parent, int w, int h, int stride) {
+  const int seg = blockIdx.y;
+  const uint8_t* c = cls + (size_t)seg * stride;
+  int* par = parent + (size_t)seg * stride;
+  const int n = w * h;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!c[i]) continue;
+    const int r = i / w, col = i % w;
+    // candidates are interior pixels, so the four backward neighbours are always in the image
+    if (c[i - 1]) uf_union(par, i, i - 1);
+    if (c[i - w - 1]) uf_union(par, i, i - w - 1);
+    if (c[i - w]) uf_union(par, i, i - w);
+    if (c[i - w + 1]) uf_union(par, i, i - w + 1);
+    (void)r;
+    (void)col;
+  }
+}
+
+__global__ void k_uf_flag(const uint8_t* __restrict__ cls, int* __restrict__ parent, uint8_t* __restrict__ strong, int n,
+                          int stride) {
+  const int seg = blockIdx.y;
+  const uint8_t* c = cls + (size_t)seg * stride;
+  int* par = parent + (size_t)seg * stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (c[i] == 2) strong[(size_t)seg * stride + uf_find(par, i)] = 1;
+}
+
+constexpr int CB = 1024;  // pixels per compaction block
+
+// mask = candidate whose component holds a strong pixel; per-block edge counts for the ordered compaction
+__global__ void __launch_bounds__(CB) k_edge_mask(const uint8_t* __restrict__ cls, int* __restrict__ parent,
+                                                  const uint8_t* __restrict__ strong, uint8_t* __restrict__ mask,
+                                                  int* __restrict__ blk_cnt, int n, int stride, int nblk) {
+  const int seg = blockIdx.y;
+  const int i = blockIdx.x * CB + threadIdx.x;
+  int e = 0;
+  if (i < n) {
+    const size_t gi = (size_t)seg * stride + i;
+    if (cls[gi]) e = strong[(size_t)seg * stride + uf_find(parent + (size_t)seg * stride, i)] ? 1 : 0;
+    mask[gi] = e ? 255 : 0;
+  }
+  int cnt = __syncthreads_count(e);
+  if (threadIdx.x == 0) blk_cnt[seg * nblk + blockIdx.x] = cnt;
+}
+
+// one CTA per frame: exclusive scan of its block counts (nblk <= a few thousand), writes the frame's edge count
+__global__ void __launch_bounds__(1024) k_seg_scan(int* __restrict__ blk_cnt, int nblk, int* __restrict__ out_count,
+                                                   int out_stride, int* __restrict__ overflow) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int seg = blockIdx.x;
+  int* b = blk_cnt + seg * nblk;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = i < nblk ? b[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int wv = warp_tot[lane], wi = wv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - wv;
+    }
+    __syncthreads();
+    int carry = carry_s;
+    int excl = carry + warp_tot[wid] + incl - v;
+    if (i < nblk) b[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int total = carry_s;
+    if (total > out_stride) {
+      atomicExch(overflow, 1);
+      total = 0;
+    }
+    out_count[seg] = total;
+  }
+}
+
+__global__ void __launch_bounds__(CB) k_scatter(const uint8_t* __restrict__ mask, const int* __restrict__ blk_off,
+                                                const float4* __restrict__ pts, const int* __restrict__ out_count,
+                                                float4* __restrict__ out, int n, int stride, int out_stride, int nblk) {
+  __shared__ int warp_tot[32];
+  const int seg = blockIdx.y;
+  if (out_count[seg] == 0) return;  // empty or overflowed frame
+  const int i = blockIdx.x * CB + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int e = (i < n) ? (mask[(size_t)seg * stride + i] != 0) : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, e);
+  if (lane == 0) warp_tot[wid] = __popc(bal);
+  __syncthreads();
+  if (wid == 0) {
+    int wv = warp_tot[lane], wi = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - wv;
+  }
+  __syncthreads();
+  if (e) {
+    int pos = blk_off[seg * nblk + blockIdx.x] + warp_tot[wid] + __popc(bal & ((1u << lane) - 1u));
+    out[(size_t)seg * out_stride + pos] = pts[(size_t)seg * stride + i];
+  }
+}
+
+}  // namespace
+
+extern "C" int rspcl_edge_extract(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_low, float t_high,
+                                  rspcl_cloud* out_edges, uint8_t* host_mask) {
+  if (!ctx || !frames || !out_edges || frames == out_edges) return RSPCL_ERR_ARG;
+  if (frames->height <= 0 || frames->width <= 0) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "edge_extract: input is not organized");
+  if (out_edges->n_seg != frames->n_seg) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "edge_extract: output n_seg mismatch");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int w = frames->width, h = frames->height, n = w * h, S = frames->n_seg, stride = frames->stride;
+  int rc = ensure_gray(ctx, const_cast<rspcl_cloud*>(frames));
+  if (rc) return rc;
+  const size_t tot = (size_t)S * stride;
+  const int nblk = div_up(n, CB);
+  uint8_t *cls = nullptr, *strong = nullptr, *mask = nullptr;
+  int *parent = nullptr, *blk = nullptr, *d_over = nullptr;
+  CU(ctx, scratch_alloc(ctx, &cls, tot));
+  CU(ctx, scratch_alloc(ctx, &strong, tot));
+  CU(ctx, scratch_alloc(ctx, &mask, tot));
+  CU(ctx, scratch_alloc(ctx, &parent, tot));
+  CU(ctx, scratch_alloc(ctx, &blk, (size_t)S * nblk));
+  CU(ctx, scratch_alloc(ctx, &d_over, 1));
+  CU(ctx, cudaMemsetAsync(strong, 0, tot, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_over, 0, sizeof(int), ctx->stream));
+
+  dim3 g1(div_up(w, TW), div_up(h, TH), S);
+  k_canny_nms<<<g1, dim3(64, 4), 0, ctx->stream>>>(frames->gray, w, h, stride, t_low, t_high, cls, parent);
+  LAUNCH_CHECK(ctx);
+  dim3 g2(blocks_per_seg(ctx, S, n, 256), S);
+  k_uf_merge<<<g2, 256, 0, ctx->stream>>>(cls, parent, w, h, stride);
+  LAUNCH_CHECK(ctx);
+  k_uf_flag<<<g2, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);
+  LAUNCH_CHECK(ctx);
+  dim3 g3(nblk, S);
+  k_edge_mask<<<g3, CB, 0, ctx->stream>>>(cls, parent, strong, mask, blk, n, stride, nblk);
+  LAUNCH_CHECK(ctx);
+  k_seg_scan<<<S, 1024, 0, ctx->stream>>>(blk, nblk, out_edges->count, out_edges->stride, d_over);
+  LAUNCH_CHECK(ctx);
+  k_scatter<<<g3, CB, 0, ctx->stream>>>(mask, blk, frames->pts, out_edges->count, out_edges->pts, n, stride,
+                                        out_edges->stride, nblk);
+  LAUNCH_CHECK(ctx);
+  out_edges->width = out_edges->height = 0;
+  out_edges->max_count_hint = out_edges->stride < n ? out_edges->stride : n;
+
+  int over = 0;
+  if (host_mask) {
+    for (int s = 0; s < S; ++s)
+      CU(ctx, cudaMemcpyAsync(host_mask + (size_t)s * n, mask + (size_t)s * stride, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+  } else if (out_edges->stride < n) {
+    // capacity below the worst case: the overflow flag must be checked (synchronises)
+    CU(ctx, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  scratch_free(ctx, cls);
+  scratch_free(ctx, strong);
+  scratch_free(ctx, mask);
+  scratch_free(ctx, parent);
+  scratch_free(ctx, blk);
+  scratch_free(ctx, d_over);
+  if (over) RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "edge_extract: a frame produced more edge points than the output stride %d", out_edges->stride);
+  return RSPCL_OK;
+}

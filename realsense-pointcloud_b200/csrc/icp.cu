@@ -1,0 +1,554 @@
+// icp.cu -- pcl::IterativeClosestPoint<PointXYZRGB,PointXYZRGB>::align for a batch of independent (source, target)
+// pairs, with PCL's DefaultConvergenceCriteria evaluated on the device.
+//
+// Reference call sites: icp:35,41-52,78-79,95,104,108-113; ndt:32,47-50,96-101; incr:37,46-49,57-61.
+// Kernels:
+//   K5  k_icp_step   fused: apply the previous incremental transform to the working source (in place, float,
+//                    un-fused -- the same rounding as PCL's transformCloud), look up the nearest target point in the
+//                    voxel-hash grid (<= 2x2x2 cells), reject beyond max_corr_dist, and reduce
+//                    {n, sum s, sum t, sum s t^T, sum d^2} (17 fp64) per CTA with warp shuffles.  No atomics: CTA
+//                    partials are combined in a fixed order so results are reproducible run to run.
+//   K5b k_icp_solve  one warp per pair: combine partials, Umeyama (3x3 Jacobi SVD, fp64), final = T * final,
+//                    DefaultConvergenceCriteria.
+// Algorithmic bytes per source point per iteration: 16 R (source) + 16 R (matched target) = 32 B; the
+// in-place update of the working cloud (16 W) and the neighbour-cell probes are overhead on top of that.
+// The "unbounded" mode (max_corr_dist larger than the grid can bin, e.g. PCL's default sqrt(DBL_MAX)) uses the
+// brute-force exact NN of grid.cu instead of the grid.
+#include "grid.cuh"
+#include <float.h>
+#include <math.h>
+
+namespace {
+
+constexpr int IT = 256;       // threads per CTA in k_icp_step
+constexpr int NRED = 17;      // n, s(3), t(3), s t^T (9), sum d2
+
+struct IcpState {  // device-resident per pair
+  float final_T[16];
+  float inc_T[16];
+  double prev_mse;
+  double mse;
+  int iterations;
+  int state;
+  int converged;
+  int done;
+  int n_corr;
+  int apply_inc;  // the working cloud still has to be moved by inc_T
+  int pad[2];
+};
+
+struct IcpDevParams {
+  int max_iterations, min_corr;
+  double max_dist_sqr, rot_thr, trans_thr, mse_abs, mse_rel;
+  float search_r;
+};
+
+__device__ __forceinline__ void mat4_identity(float* T) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+}
+
+// ---- 3x3 one-sided Jacobi SVD in fp64: A = U diag(s) V^T, s descending (row-major)
+__device__ void svd3(const double* A_in, double* U, double* s, double* V) {
+  double B[9];
+  for (int i = 0; i < 9; ++i) B[i] = A_in[i];
+  for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int k = 0; k < 3; ++k) {
+          alpha += B[k * 3 + p] * B[k * 3 + p];
+          beta += B[k * 3 + q] * B[k * 3 + q];
+          gamma += B[k * 3 + p] * B[k * 3 + q];
+        }
+        if (gamma == 0.0 || fabs(gamma) <= DBL_EPSILON * sqrt(alpha * beta)) continue;
+        rotated = true;
+        double zeta = (beta - alpha) / (2.0 * gamma);
+        double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int k = 0; k < 3; ++k) {
+          double bp = B[k * 3 + p], bq = B[k * 3 + q];
+          B[k * 3 + p] = c * bp - sn * bq;
+          B[k * 3 + q] = sn * bp + c * bq;
+          double vp = V[k * 3 + p], vq = V[k * 3 + q];
+          V[k * 3 + p] = c * vp - sn * vq;
+          V[k * 3 + q] = sn * vp + c * vq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double nrm[3];
+  for (int j = 0; j < 3; ++j) nrm[j] = sqrt(B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j]);
+  int o0 = 0, o1 = 1, o2 = 2, tmp;
+  if (nrm[o0] < nrm[o1]) { tmp = o0; o0 = o1; o1 = tmp; }
+  if (nrm[o1] < nrm[o2]) { tmp = o1; o1 = o2; o2 = tmp; }
+  if (nrm[o0] < nrm[o1]) { tmp = o0; o0 = o1; o1 = tmp; }
+  const int ord[3] = {o0, o1, o2};
+  double Bs[9], Vs[9];
+  for (int j = 0; j < 3; ++j) {
+    s[j] = nrm[ord[j]];
+    for (int k = 0; k < 3; ++k) {
+      Bs[k * 3 + j] = B[k * 3 + ord[j]];
+      Vs[k * 3 + j] = V[k * 3 + ord[j]];
+    }
+  }
+  for (int i = 0; i < 9; ++i) V[i] = Vs[i];
+  const double tiny = s[0] * DBL_EPSILON * 8.0;
+  int rank = 0;
+  for (int j = 0; j < 3; ++j) {
+    if (s[j] > tiny && s[j] > 0.0) {
+      for (int k = 0; k < 3; ++k) U[k * 3 + j] = Bs[k * 3 + j] / s[j];
+      rank = j + 1;
+    } else {
+      break;
+    }
+  }
+  if (rank == 0) {
+    for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  } else if (rank == 1) {
+    double u0[3] = {U[0], U[3], U[6]};
+    int m = 0;
+    if (fabs(u0[1]) < fabs(u0[m])) m = 1;
+    if (fabs(u0[2]) < fabs(u0[m])) m = 2;
+    double e[3] = {0, 0, 0};
+    e[m] = 1;
+    double u1[3] = {u0[1] * e[2] - u0[2] * e[1], u0[2] * e[0] - u0[0] * e[2], u0[0] * e[1] - u0[1] * e[0]};
+    double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    for (int k = 0; k < 3; ++k) u1[k] /= n1;
+    double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+    for (int k = 0; k < 3; ++k) {
+      U[k * 3 + 1] = u1[k];
+      U[k * 3 + 2] = u2[k];
+    }
+  } else if (rank == 2) {
+    double u0[3] = {U[0], U[3], U[6]}, u1[3] = {U[1], U[4], U[7]};
+    double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+    double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    for (int k = 0; k < 3; ++k) U[k * 3 + 2] = u2[k] / n2;
+  }
+}
+
+__device__ __forceinline__ double det3(const double* M) {
+  return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+// pcl::umeyama(src, dst, with_scaling=false) from raw fp64 moments: S = {n, sum s, sum t, sum s_r t_c}
+__device__ void umeyama_from_moments(const double* S, float* T) {
+  const double n = S[0], inv_n = 1.0 / n;
+  const double ms[3] = {S[1] * inv_n, S[2] * inv_n, S[3] * inv_n};
+  const double mt[3] = {S[4] * inv_n, S[5] * inv_n, S[6] * inv_n};
+  double sigma[9];  // sigma(r,c) = mean((t_r - mt_r)(s_c - ms_c))
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) sigma[r * 3 + c] = S[7 + c * 3 + r] * inv_n - mt[r] * ms[c];
+  double U[9], sv[3], V[9];
+  svd3(sigma, U, sv, V);
+  const double d = det3(U) * det3(V);
+  const double Sd[3] = {1.0, 1.0, d < 0 ? -1.0 : 1.0};
+  double R[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double acc = 0;
+      for (int k = 0; k < 3; ++k) acc += U[r * 3 + k] * Sd[k] * V[c * 3 + k];
+      R[r * 3 + c] = acc;
+    }
+  mat4_identity(T);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T[c * 4 + r] = (float)R[r * 3 + c];
+    T[12 + r] = (float)(mt[r] - (R[r * 3 + 0] * ms[0] + R[r * 3 + 1] * ms[1] + R[r * 3 + 2] * ms[2]));
+  }
+}
+
+// C = A * B (column-major float), entries ((a0 b0 + a1 b1) + a2 b2) + a3 b3 un-fused, as the oracle
+__device__ void mat4_mul(const float* A, const float* B, float* C) {
+  float R[16];
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r) {
+      float s = fmul(A[0 * 4 + r], B[c * 4 + 0]);
+      s = fadd(s, fmul(A[1 * 4 + r], B[c * 4 + 1]));
+      s = fadd(s, fmul(A[2 * 4 + r], B[c * 4 + 2]));
+      s = fadd(s, fmul(A[3 * 4 + r], B[c * 4 + 3]));
+      R[c * 4 + r] = s;
+    }
+  for (int i = 0; i < 16; ++i) C[i] = R[i];
+}
+
+__global__ void k_icp_init(IcpState* __restrict__ st, const float* __restrict__ guess, const double* __restrict__ prev_mse,
+                           int n_seg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  IcpState S;
+  if (guess)
+    for (int i = 0; i < 16; ++i) S.final_T[i] = guess[s * 16 + i];
+  else
+    mat4_identity(S.final_T);
+  bool ident = true;
+  for (int i = 0; i < 16; ++i)
+    if (S.final_T[i] != ((i % 5 == 0) ? 1.f : 0.f)) ident = false;
+  // the first k_icp_step moves the source by the guess (icp.hpp: transformCloud(*input_, *input_transformed, guess))
+  for (int i = 0; i < 16; ++i) S.inc_T[i] = S.final_T[i];
+  S.apply_inc = ident ? 0 : 1;
+  S.prev_mse = prev_mse[s];
+  S.mse = 0.0;
+  S.iterations = 0;
+  S.state = RSPCL_CONV_NOT_CONVERGED;
+  S.converged = 0;
+  S.done = 0;
+  S.n_corr = 0;
+  S.pad[0] = S.pad[1] = 0;
+  st[s] = S;
+}
+
+template <bool BRUTE>
+__global__ void __launch_bounds__(IT) k_icp_step(float4* __restrict__ work, const int* __restrict__ count, int stride,
+                                                 const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
+                                                 const float4* __restrict__ tgt, const int* __restrict__ tcount,
+                                                 int tstride, double* __restrict__ partials,
+                                                 int* __restrict__ first_corr) {
+  __shared__ float M[16];
+  __shared__ double s_red[IT / 32][NRED];
+  __shared__ float4 tile[BRUTE ? IT : 1];
+  const int seg = blockIdx.y;
+  if (st[seg].done) return;
+  const int n = count[seg];
+  const int apply = st[seg].apply_inc;
+  if (threadIdx.x < 16) M[threadIdx.x] = st[seg].inc_T[threadIdx.x];
+  __syncthreads();
+  const bool want_corr = first_corr != nullptr && st[seg].iterations == 0;
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+
+  const int tseg = g.shared_target ? 0 : seg;
+  const int nt = BRUTE ? tcount[tseg] : 0;
+  for (int base = blockIdx.x * IT; base < n; base += gridDim.x * IT) {  // block-uniform trip count
+    const int i = base + threadIdx.x;
+    float4 p = make_float4(NAN, NAN, NAN, 0.f);
+    if (i < n) {
+      p = work[(size_t)seg * stride + i];
+      if (apply && finite3(p.x, p.y, p.z)) {
+        const float3 q = xform_point(M, p.x, p.y, p.z);
+        p.x = q.x;
+        p.y = q.y;
+        p.z = q.z;
+        work[(size_t)seg * stride + i] = p;
+      }
+    }
+    int j = -1;
+    float d2 = INFINITY;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BRUTE) {
+      const float4* T = tgt + (size_t)tseg * tstride;
+      for (int tb = 0; tb < nt; tb += IT) {
+        __syncthreads();
+        if (tb + threadIdx.x < nt) tile[threadIdx.x] = T[tb + threadIdx.x];
+        __syncthreads();
+        const int m = min(IT, nt - tb);
+        for (int k = 0; k < m; ++k) {
+          const float4 c = tile[k];
+          const float d = dist2_l2simple(p.x, p.y, p.z, c.x, c.y, c.z);
+          if (d < d2) {
+            d2 = d;
+            j = tb + k;
+            t = c;
+          }
+        }
+      }
+    } else if (i < n && finite3(p.x, p.y, p.z)) {
+      j = grid_nn_bounded(g, seg, p.x, p.y, p.z, prm.search_r, &d2, &t);
+    }
+    const bool ok = (i < n) && j >= 0 && !((double)d2 > prm.max_dist_sqr);
+    if (want_corr && i < n) first_corr[(size_t)seg * stride + i] = ok ? j : -1;
+    if (ok) {
+      const double sx = p.x, sy = p.y, sz = p.z, tx = t.x, ty = t.y, tz = t.z;
+      acc[0] += 1.0;
+      acc[1] += sx; acc[2] += sy; acc[3] += sz;
+      acc[4] += tx; acc[5] += ty; acc[6] += tz;
+      acc[7] += sx * tx; acc[8] += sx * ty; acc[9] += sx * tz;
+      acc[10] += sy * tx; acc[11] += sy * ty; acc[12] += sy * tz;
+      acc[13] += sz * tx; acc[14] += sz * ty; acc[15] += sz * tz;
+      acc[16] += (double)d2;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < IT / 32; ++w) v += s_red[w][threadIdx.x];
+    partials[((size_t)seg * gridDim.x + blockIdx.x) * NRED + threadIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(32) k_icp_solve(IcpState* __restrict__ st, const double* __restrict__ partials, int nblk,
+                                                  IcpDevParams prm, int* __restrict__ n_active) {
+  const int seg = blockIdx.x;
+  IcpState* S = &st[seg];
+  if (S->done) return;
+  const int lane = threadIdx.x;
+  // combine CTA partials: lane k sums quantity k over the blocks in ascending order (fixed order -> deterministic)
+  double v = 0;
+  if (lane < NRED)
+    for (int b = 0; b < nblk; ++b) v += partials[((size_t)seg * nblk + b) * NRED + lane];
+  __shared__ double sums[NRED];
+  if (lane < NRED) sums[lane] = v;
+  __syncwarp();
+  if (lane != 0) return;
+  S->apply_inc = 0;
+  const int n_corr = (int)(sums[0] + 0.5);
+  S->n_corr = n_corr;
+  if (n_corr < prm.min_corr) {
+    // icp.hpp: "Not enough correspondences found" -> NO_CORRESPONDENCES, converged_ = false, loop exits
+    S->state = RSPCL_CONV_NO_CORRESPONDENCES;
+    S->converged = 0;
+    S->done = 1;
+    atomicSub(n_active, 1);
+    return;
+  }
+  float T[16];
+  umeyama_from_moments(sums, T);
+  for (int i = 0; i < 16; ++i) S->inc_T[i] = T[i];
+  S->apply_inc = 1;
+  mat4_mul(T, S->final_T, S->final_T);
+  const int it = ++S->iterations;
+  const double mse = sums[16] / (double)n_corr;
+  S->mse = mse;
+  // DefaultConvergenceCriteria::hasConverged
+  int state = RSPCL_CONV_NOT_CONVERGED;
+  bool conv = false;
+  if (it >= prm.max_iterations) {
+    state = RSPCL_CONV_ITERATIONS;
+    conv = true;
+  } else {
+    const double cos_angle = 0.5 * (double)(fadd(fadd(fadd(T[0], T[5]), T[10]), -1.0f));
+    const double tr2 = (double)fadd(fadd(fmul(T[12], T[12]), fmul(T[13], T[13])), fmul(T[14], T[14]));
+    if (cos_angle >= prm.rot_thr && tr2 <= prm.trans_thr) {
+      state = RSPCL_CONV_TRANSFORM;
+      conv = true;
+    } else {
+      const double prev = S->prev_mse;
+      if (fabs(mse - prev) < prm.mse_abs) {
+        state = RSPCL_CONV_ABS_MSE;
+        conv = true;
+      } else if (fabs(mse - prev) / prev < prm.mse_rel) {
+        state = RSPCL_CONV_REL_MSE;
+        conv = true;
+      } else {
+        S->prev_mse = mse;
+      }
+    }
+  }
+  S->state = state;
+  if (conv) {
+    S->converged = 1;
+    S->done = 1;
+    atomicSub(n_active, 1);
+  }
+}
+
+__global__ void k_copy_work(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
+                            float4* __restrict__ work, int stride_work) {
+  const int seg = blockIdx.y;
+  const int n = count[seg];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    work[(size_t)seg * stride_work + i] = src[(size_t)seg * stride_src + i];
+}
+
+__global__ void k_gather_final(const IcpState* __restrict__ st, float* __restrict__ T, int n_seg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seg * 16) T[i] = st[i / 16].final_T[i % 16];
+}
+
+__global__ void k_pack_i32(const int* __restrict__ v, const int* __restrict__ count, const int* __restrict__ off, int stride,
+                           int* __restrict__ out) {
+  const int seg = blockIdx.y;
+  const int n = count[seg];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[off[seg] + i] = v[(size_t)seg * stride + i];
+}
+
+}  // namespace
+
+extern "C" void rspcl_icp_reference_params(rspcl_icp_params* p) {
+  p->max_iterations = 100;              // icp:42
+  p->min_correspondences = 3;
+  p->max_corr_dist = 0.01;              // icp:43
+  p->transformation_epsilon = 1;        // icp:44
+  p->euclidean_fitness_epsilon = 1000;  // icp:45
+  p->mse_threshold_absolute = 1e-12;
+}
+
+// Device-level align used by rspcl_icp_align and the pairwise pipeline.  d_guess: n_seg x 16 floats on the device or
+// null.  h_results: host array (prev_mse read as input).  Synchronises before returning.
+int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
+                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, int* d_first_corr) {
+  const int S = src->n_seg;
+  const int shared_target = (tgt->n_seg == 1 && S > 1) ? 1 : 0;
+  if (!shared_target && tgt->n_seg != S) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "icp_align: src has %d segments, tgt %d", S, tgt->n_seg);
+  if (aligned && (aligned->n_seg != S || aligned->stride < src->max_count_hint))
+    RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "icp_align: aligned output too small");
+  if (prm->max_iterations < 1) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "icp_align: max_iterations < 1");
+
+  IcpDevParams dp;
+  dp.max_iterations = prm->max_iterations;
+  dp.min_corr = prm->min_correspondences;
+  dp.max_dist_sqr = prm->max_corr_dist * prm->max_corr_dist;
+  dp.rot_thr = 1.0 - prm->transformation_epsilon;
+  dp.trans_thr = prm->transformation_epsilon;
+  dp.mse_abs = prm->mse_threshold_absolute;
+  dp.mse_rel = prm->euclidean_fitness_epsilon;
+  // grid mode needs cells of ~2x the gate that still fit the 16-bit cell coordinates; otherwise brute force
+  const bool brute = !(prm->max_corr_dist > 0.0 && prm->max_corr_dist < 5.0);
+  const float cs = brute ? 1.f : (float)(prm->max_corr_dist * 2.05);
+  dp.search_r = brute ? 0.f : (float)(prm->max_corr_dist * 1.01);
+
+  const int wstride = src->stride ? src->stride : 1;
+  float4* work = nullptr;
+  IcpState* st = nullptr;
+  double *partials = nullptr, *d_prev = nullptr;
+  int *n_active = nullptr, *d_range = nullptr;
+  float* d_T = nullptr;
+  const int nblk = blocks_per_seg(ctx, S, src->max_count_hint, IT);
+  CU(ctx, scratch_alloc(ctx, &work, (size_t)S * wstride));
+  CU(ctx, scratch_alloc(ctx, &st, (size_t)S));
+  CU(ctx, scratch_alloc(ctx, &partials, (size_t)S * nblk * NRED));
+  CU(ctx, scratch_alloc(ctx, &d_prev, (size_t)S));
+  CU(ctx, scratch_alloc(ctx, &n_active, 1));
+  CU(ctx, scratch_alloc(ctx, &d_range, 1));
+  CU(ctx, scratch_alloc(ctx, &d_T, (size_t)S * 16));
+  std::vector<double> prev(S);
+  for (int s = 0; s < S; ++s) prev[s] = h_results[s].prev_mse;
+  CU(ctx, cudaMemcpyAsync(d_prev, prev.data(), S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(n_active, &S, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_range, 0, sizeof(int), ctx->stream));
+  k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, S);
+  LAUNCH_CHECK(ctx);
+  dim3 gcopy(blocks_per_seg(ctx, S, src->max_count_hint, 256), S);
+  k_copy_work<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, work, wstride);
+  LAUNCH_CHECK(ctx);
+
+  DevGrid g;
+  g.shared_target = shared_target;
+  if (!brute) {
+    int rc = grid_build(ctx, tgt, cs, &g, d_range);
+    if (rc) return rc;
+  }
+
+  // iteration loop: launches are enqueued in growing chunks; the host only looks at the active-pair counter
+  // between chunks (1, 1, 2, 4, 8, ... iterations), so the reference's one-iteration aligns cost one read-back.
+  dim3 gstep(nblk, S);
+  int done_iters = 0, chunk = 1, active = S;
+  while (done_iters < prm->max_iterations && active > 0) {
+    const int todo = (chunk < prm->max_iterations - done_iters) ? chunk : prm->max_iterations - done_iters;
+    for (int k = 0; k < todo; ++k) {
+      if (brute)
+        k_icp_step<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count, tgt->stride,
+                                                       partials, d_first_corr);
+      else
+        k_icp_step<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count, tgt->stride,
+                                                        partials, d_first_corr);
+      LAUNCH_CHECK(ctx);
+      k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, partials, nblk, dp, n_active);
+      LAUNCH_CHECK(ctx);
+    }
+    done_iters += todo;
+    CU(ctx, cudaMemcpyAsync(&active, n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (done_iters > 1) chunk *= 2;
+  }
+
+  // results + aligned output (Registration::align: output = final applied to the original source)
+  std::vector<IcpState> hst(S);
+  int range = 0;
+  CU(ctx, cudaMemcpyAsync(hst.data(), st, S * sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(&range, d_range, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = RSPCL_OK;
+  if (aligned) {
+    k_gather_final<<<div_up(S * 16, 256), 256, 0, ctx->stream>>>(st, d_T, S);
+    LAUNCH_CHECK(ctx);
+    rc = transform_device(ctx, src, d_T, 0, aligned);
+  }
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < S; ++s) {
+    memcpy(h_results[s].T, hst[s].final_T, sizeof(float) * 16);
+    h_results[s].converged = hst[s].converged;
+    h_results[s].state = hst[s].state;
+    h_results[s].iterations = hst[s].iterations;
+    h_results[s].n_corr = hst[s].n_corr;
+    h_results[s].mse = hst[s].mse;
+    h_results[s].prev_mse = hst[s].prev_mse;
+  }
+  if (!brute) grid_free(ctx, &g);
+  scratch_free(ctx, work);
+  scratch_free(ctx, st);
+  scratch_free(ctx, partials);
+  scratch_free(ctx, d_prev);
+  scratch_free(ctx, n_active);
+  scratch_free(ctx, d_range);
+  scratch_free(ctx, d_T);
+  if (rc) return rc;
+  if (range) RSPCL_FAIL(ctx, RSPCL_ERR_RANGE, "icp_align: target coordinates exceed the grid key range (+-32767 cells of %g m)", cs);
+  return RSPCL_OK;
+}
+
+int refresh_count_hint(rspcl_ctx* ctx, const rspcl_cloud* c, std::vector<int>* counts_out) {
+  std::vector<int> cnt(c->n_seg);
+  CU(ctx, cudaMemcpyAsync(cnt.data(), c->count, c->n_seg * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  int m = 0;
+  for (int v : cnt) m = v > m ? v : m;
+  const_cast<rspcl_cloud*>(c)->max_count_hint = m;
+  if (counts_out) counts_out->swap(cnt);
+  return RSPCL_OK;
+}
+
+extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
+                               const float* guess, rspcl_icp_result* results, rspcl_cloud* aligned, int32_t* first_corr) {
+  if (!ctx || !src || !tgt || !prm || !results) return RSPCL_ERR_ARG;
+  if (aligned == tgt) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "icp_align: aligned must not alias the target");
+  CU(ctx, cudaSetDevice(ctx->device));
+  std::vector<int> scnt;
+  int rc = refresh_count_hint(ctx, src, &scnt);
+  if (rc) return rc;
+  rc = refresh_count_hint(ctx, tgt, nullptr);
+  if (rc) return rc;
+  const int S = src->n_seg;
+  float* d_guess = nullptr;
+  int* d_fc = nullptr;
+  if (guess) {
+    CU(ctx, scratch_alloc(ctx, &d_guess, (size_t)S * 16));
+    CU(ctx, cudaMemcpyAsync(d_guess, guess, (size_t)S * 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (first_corr) CU(ctx, scratch_alloc(ctx, &d_fc, (size_t)S * (src->stride ? src->stride : 1)));
+  rc = icp_align_device(ctx, src, tgt, prm, d_guess, results, aligned, d_fc);
+  if (!rc && first_corr) {
+    std::vector<int> off(S);
+    long long total = 0;
+    for (int s = 0; s < S; ++s) {
+      off[s] = (int)total;
+      total += scnt[s];
+    }
+    if (total) {
+      int *d_off = nullptr, *packed = nullptr;
+      CU(ctx, scratch_alloc(ctx, &d_off, (size_t)S));
+      CU(ctx, scratch_alloc(ctx, &packed, (size_t)total));
+      CU(ctx, cudaMemcpyAsync(d_off, off.data(), S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      dim3 grid(blocks_per_seg(ctx, S, src->max_count_hint, 256), S);
+      k_pack_i32<<<grid, 256, 0, ctx->stream>>>(d_fc, src->count, d_off, src->stride, packed);
+      LAUNCH_CHECK(ctx);
+      CU(ctx, cudaMemcpyAsync(first_corr, packed, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(ctx, cudaStreamSynchronize(ctx->stream));
+      scratch_free(ctx, d_off);
+      scratch_free(ctx, packed);
+    }
+  }
+  scratch_free(ctx, d_guess);
+  scratch_free(ctx, d_fc);
+  return rc;
+}
