@@ -37,7 +37,9 @@ def rigid(rng, ang=0.2, tr=0.1):
 
 def pose_err(A, B):
     D = np.linalg.inv(np.asarray(A, np.float64)) @ np.asarray(B, np.float64)
-    return np.arccos(np.clip((np.trace(D[:3, :3]) - 1) / 2, -1, 1)), np.linalg.norm(D[:3, 3])
+    # atan2 of the skew part: well conditioned for tiny angles (acos(1 - 1e-8) would already read 1.4e-4 rad)
+    sk = np.linalg.norm([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]]) / 2
+    return np.arctan2(sk, (np.trace(D[:3, :3]) - 1) / 2), np.linalg.norm(D[:3, 3])
 
 
 def forced(n_iter):
