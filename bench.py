@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pair registrations/s @640x480 (BASELINE.json metric) on N B200s of one node.
+
+A step = one pass of the registration hot path over one synthetic sweep per GPU: F organized 640x480 RGB-D frames
+(307,200 points each) -> F-1 pairwise edge-based ICP registrations (frame k onto frame k-1, BASELINE configs[1]
+settings: -30 deg initial guess, 50 forced coarse + 50 forced fine iterations, 1 cm approximate voxel filter,
+1 cm correspondence gate) including the full-cloud transformPointCloud of every source frame.
+
+  value  : device-resident throughput (frames already in HBM as device clouds), CUDA events on the library stream.
+  e2e    : the same step through the C ABI with HOST buffers: pinned pcl::PointXYZRGB (32 B/pt) frames uploaded and the
+           transformed full clouds downloaded inside the timed region.
+  roofline: the ICP correspondence+reduction kernel (k_icp_step), algorithmic bytes = 32 B per source point per
+           iteration, timed with CUDA events bracketing each launch in one extra, untimed-for-`value` step.
+  cpu_baseline: the oracle (CPU port of the reference's PCL path) on a bounded sample of the same sweep, 1 thread.
+  --impl reference: the oracle with all host threads (one pair per thread) -- the reference arm.
+
+Multi-GPU: independent sweeps, one per rank (pair-sharded, no data-path collective) -> "scaling": "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for sub in ("tools", "realsense-pointcloud_b200"):
+    sys.path.insert(0, os.path.join(ROOT, sub))
+
+W, H = 640, 480
+NPX = W * H
+RADS = -0.523599  # icp_edge_based_registration.hpp:135
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=33, help="frames per GPU sweep (pairs = frames - 1)")
+    ap.add_argument("--iters", type=int, default=50, help="forced ICP iterations per stage (configs[1]: 50)")
+    ap.add_argument("--coarse", default="icp", choices=["icp", "ndt"])
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--cpu-pairs", type=int, default=24, help="pairs in the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def forced_kw(iters):
+    return dict(max_iterations=iters, transformation_epsilon=-1.0, euclidean_fitness_epsilon=-1e300,
+                mse_threshold_absolute=-1.0)
+
+
+def guess_matrix():
+    import gen_scene
+    g = np.eye(4)
+    g[:3, :3] = gen_scene.rot_y(RADS)
+    return g
+
+
+def pose_err(A, B):
+    D = np.linalg.inv(np.asarray(A, np.float64)) @ np.asarray(B, np.float64)
+    sk = np.linalg.norm([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]]) / 2
+    return float(np.arctan2(sk, (np.trace(D[:3, :3]) - 1) / 2)), float(np.linalg.norm(D[:3, 3]))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU (oracle) legs
+def cpu_sweep_pairs(frames, n_pairs, iters, coarse, threads):
+    """Oracle restatement of the same step on `n_pairs` pairs; returns (seconds, transforms).  TEST-INFRA use of
+    oracle/ permitted here (cpu_baseline leg / reference arm only)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from concurrent.futures import ThreadPoolExecutor
+    prm = orc.icp_params(**forced_kw(iters))
+    ndt = orc.ndt_params()
+    guess = guess_matrix()
+    orc.lib()
+
+    def feat(k):
+        e, _ = orc.extract_edges(frames[k], W, H)
+        return orc.approx_voxel(e)
+
+    def reg(i, feats):
+        src, tgt = feats[i + 1], feats[i]
+        if coarse == "ndt":
+            c = orc.ndt_align(src, tgt, ndt, guess=guess)
+        else:
+            c = orc.icp_align(src, tgt, prm, guess=guess)
+        f = orc.icp_align(c["aligned"], tgt, prm)
+        if f["converged"]:
+            orc.transform(orc.transform(frames[i + 1], c["T"]), f["T"])
+        return f["T"].astype(np.float64) @ c["T"].astype(np.float64)
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        feats = [feat(k) for k in range(n_pairs + 1)]
+        Ts = [reg(i, feats) for i in range(n_pairs)]
+    else:
+        with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL inside the oracle calls
+            feats = list(ex.map(feat, range(n_pairs + 1)))
+            Ts = list(ex.map(lambda i: reg(i, feats), range(n_pairs)))
+    return time.perf_counter() - t0, Ts
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    import gen_scene
+    threads = host_threads()
+    n_pairs = max(8, min(2 * threads, 64))
+    frames, _ = gen_scene.make_sweep(a.seed, min(n_pairs + 1, 17))
+    # bounded sample: reuse the generated frames cyclically so generation stays short
+    idx = [k % len(frames) for k in range(n_pairs + 1)]
+    fr = [frames[k] for k in idx]
+    for _ in range(a.warmup):
+        cpu_sweep_pairs(fr, min(n_pairs, threads), a.iters, a.coarse, threads)
+    total = 0.0
+    for _ in range(a.steps):
+        dt, _ = cpu_sweep_pairs(fr, n_pairs, a.iters, a.coarse, threads)
+        total += dt
+    val = a.steps * n_pairs / total
+    sample = "%d pairs/step x %d steps, %d threads (one pair per thread), oracle port of the PCL path" % (n_pairs, a.steps, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "frame-pair registrations/sec @640x480", "value": val, "unit": "pairs/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, n_pairs + 1),
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(a, frames):
+    return {"workload": "configs[1] batched: pairwise edge-based ICP over a %d-frame 640x480 sweep per GPU "
+                        "(%d pairs/step), %d forced coarse + %d forced fine iterations, -30deg guess, 1cm voxel, "
+                        "1cm gate, full-cloud transform" % (frames, frames - 1, a.iters, a.iters),
+            "frames_per_gpu": frames, "pairs_per_step_per_gpu": frames - 1, "points_per_frame": NPX,
+            "coarse": a.coarse, "icp_iterations": [a.iters, a.iters],
+            "l2": "inputs larger than L2 (%.0f MB of frames per step vs 126 MB L2)" % (frames * NPX * 16 / 1e6),
+            "parallelism": "pair-sharded x%d (independent sweeps, no collective)" % a.gpus}
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+
+    import torch
+    import gen_scene
+    import rspcl_b200 as R
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    ctx = R.Context(dev)
+
+    F = a.frames
+    n_pairs = F - 1
+    frames, Tgt = gen_scene.make_sweep(a.seed + 1000 * rank, F)
+    guess = guess_matrix()
+    icp = R.icp_params(**forced_kw(a.iters))
+    ndt = R.ndt_params()
+    coarse = R.COARSE_NDT if a.coarse == "ndt" else R.COARSE_ICP
+    src_idx = np.arange(1, F, dtype=np.int32)
+    tgt_idx = np.arange(0, F - 1, dtype=np.int32)
+
+    # pinned host frames in pcl::PointXYZRGB layout (what the reference holds in memory) + pinned result buffer
+    h_in = ctx.pinned(F * NPX * 32)
+    h_in.view(R.PCL32)[:] = np.concatenate([R.to_pcl32(f) for f in frames])
+    h_out = ctx.pinned(n_pairs * NPX * 32)
+    counts = np.full(F, NPX, np.int32)
+    d_frames = ctx.cloud(F, NPX)
+    d_out = ctx.cloud(n_pairs, NPX)
+    out_counts = np.zeros(n_pairs, np.int32)
+    L = R.lib()
+    import ctypes as C
+
+    def upload():
+        d_frames.upload_raw(h_in.ctypes.data_as(C.c_void_p), counts, W, H, R.LAYOUT_PCL32)
+
+    def step():
+        return R.register_pairs(ctx, d_frames, src_idx, tgt_idx, coarse, icp=icp, ndt=ndt, guess=guess, out_transformed=d_out)
+
+    def download():
+        ctx.check(L.rspcl_cloud_download(ctx.h, d_out.h, h_out.ctypes.data_as(C.c_void_p), R.LAYOUT_PCL32,
+                                         C.c_longlong(n_pairs * NPX), out_counts.ctypes.data_as(C.c_void_p)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- correctness guard: every pair converges and lands near the ground truth
+    upload()
+    res = step()
+    n_conv = sum(int(r.converged) for r in res)
+    errs = []
+    for i in range(n_pairs):
+        T = R.c_to_mat(res[i].T_fine).astype(np.float64) @ R.c_to_mat(res[i].T_coarse).astype(np.float64)
+        errs.append(pose_err(T, gen_scene.pairwise_gt(Tgt, i + 1)))
+    max_ang, max_tr = max(e[0] for e in errs), max(e[1] for e in errs)
+    if n_conv != n_pairs or max_ang > 0.01 or max_tr > 0.02:
+        raise SystemExit("bench sanity check failed: converged %d/%d, max err %.4g rad %.4g m" % (n_conv, n_pairs, max_ang, max_tr))
+    mean_src = float(np.mean([r.n_src for r in res]))
+
+    # ---- device-resident throughput
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        step()
+    ms = ctx.timer_stop()
+    l1 = ctx.launches()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    value = world * n_pairs * a.steps / (ms / 1e3)
+
+    # ---- end to end through the C ABI with host buffers
+    for _ in range(max(1, a.warmup - 1)):
+        upload(); step(); download()
+    barrier()
+    ctx.timer_start()
+    for _ in range(a.steps):
+        upload()
+        step()
+        download()
+    ms_e2e = max_over_ranks(ctx.timer_stop())
+    barrier()
+    e2e = world * n_pairs * a.steps / (ms_e2e / 1e3)
+    assert int(out_counts.sum()) == n_pairs * NPX
+
+    # ---- roofline of the dominant kernel, from per-launch CUDA events in one extra profiled step
+    ctx.profile_reset()
+    ctx.profile(True)
+    ctx.timer_start()
+    step()
+    ms_prof = ctx.timer_stop()
+    ctx.profile(False)
+    kern = {k: ctx.profile_get(k) for k in ("k_icp_step", "k_icp_solve", "grid_build", "k_canny_nms",
+                                            "edge_hysteresis_compact", "k_approx_voxel", "k_transform2", "k_ndt_eval",
+                                            "ndt_voxel_build")}
+    ki = kern["k_icp_step"]
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = 32.0 * ki["units"] / (ki["ms"] / 1e3) / 1e9 if ki["ms"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "icp_step_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"kernel": "k_icp_step", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": 32.0 * ki["units"] / max(ki["launches"], 1),
+                "avg_launch_us": 1e3 * ki["ms"] / max(ki["launches"], 1), "launches_per_step": ki["launches"],
+                "share_of_step": ki["ms"] / ms_prof if ms_prof > 0 else None,
+                "note": "working set of a pair (~10^4 points) is L2-resident; single launches are latency-bound (SURVEY H3)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle, one thread, bounded sample of the same sweep
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        m = min(a.cpu_pairs, n_pairs)
+        dt, Tcpu = cpu_sweep_pairs(list(frames[:m + 1]), m, a.iters, a.coarse, 1)
+        worst = 0.0
+        for i in range(m):
+            T = R.c_to_mat(res[i].T_fine).astype(np.float64) @ R.c_to_mat(res[i].T_coarse).astype(np.float64)
+            ang, tr = pose_err(T, Tcpu[i])
+            worst = max(worst, ang, tr)
+        cpu = {"value": m / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+               "sample": "first %d pairs of the same sweep, single thread (the reference path is single-threaded), %.1f s; "
+                         "max |GPU - CPU| transform difference %.2e (rad or m)" % (m, dt, worst),
+               "host_threads_available": host_threads()}
+
+    if rank == 0:
+        out = {
+            "metric": "frame-pair registrations/sec @640x480", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, F),
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": F * NPX * 32,
+                    "d2h_bytes_per_step": n_pairs * NPX * 32 + n_pairs * 160, "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": int(l1 - l0),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "kernels_ms_per_step": {k: v["ms"] for k, v in kern.items() if v["launches"]},
+            "ms_per_icp_iteration": (kern["k_icp_step"]["ms"] + kern["k_icp_solve"]["ms"]) / max(kern["k_icp_step"]["launches"], 1),
+            "check": {"pairs_converged": n_conv, "max_err_vs_ground_truth": [max_ang, max_tr],
+                      "mean_source_edge_points": mean_src},
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

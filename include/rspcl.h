@@ -46,6 +46,13 @@ int rspcl_timer_start(rspcl_ctx* ctx);
 int rspcl_timer_stop(rspcl_ctx* ctx, float* elapsed_ms);   /* synchronises */
 /* number of kernels this library has launched on the context since creation */
 long long rspcl_launch_count(const rspcl_ctx* ctx);
+/* Per-kernel CUDA-event profile (off by default).  While enabled, the library brackets the launches of its main
+ * kernels with events on the context stream and accumulates {elapsed ms, launches, work units}.  `kernel` is the
+ * kernel name, e.g. "k_icp_step" (units = source points), "k_ndt_eval" (source points), "k_canny_nms" (pixels),
+ * "k_transform2" (points), "k_approx_voxel" (points), "k_unpack" (points).  rspcl_profile_get synchronises. */
+int rspcl_profile_enable(rspcl_ctx* ctx, int on);
+int rspcl_profile_reset(rspcl_ctx* ctx);
+int rspcl_profile_get(rspcl_ctx* ctx, const char* kernel, double* total_ms, long long* launches, double* units);
 /* pinned host memory for e2e transfers */
 int rspcl_host_alloc(rspcl_ctx* ctx, size_t bytes, void** out);
 int rspcl_host_free(rspcl_ctx* ctx, void* p);

@@ -69,6 +69,47 @@ extern "C" int rspcl_timer_stop(rspcl_ctx* ctx, float* ms) {
 }
 extern "C" long long rspcl_launch_count(const rspcl_ctx* ctx) { return ctx->launches; }
 
+static int prof_drain(rspcl_ctx* ctx) {
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& acc = ctx->prof_acc[ctx->prof_names[r.kernel]];
+      acc.ms += ms;
+      acc.launches += 1;
+      acc.units += r.units;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->prof_recs.clear();
+  return RSPCL_OK;
+}
+extern "C" int rspcl_profile_enable(rspcl_ctx* ctx, int on) {
+  if (!ctx) return RSPCL_ERR_ARG;
+  int rc = prof_drain(ctx);
+  ctx->prof_on = on != 0;
+  return rc;
+}
+extern "C" int rspcl_profile_reset(rspcl_ctx* ctx) {
+  if (!ctx) return RSPCL_ERR_ARG;
+  int rc = prof_drain(ctx);
+  ctx->prof_acc.clear();
+  return rc;
+}
+extern "C" int rspcl_profile_get(rspcl_ctx* ctx, const char* kernel, double* total_ms, long long* launches, double* units) {
+  if (!ctx || !kernel) return RSPCL_ERR_ARG;
+  int rc = prof_drain(ctx);
+  if (rc) return rc;
+  auto it = ctx->prof_acc.find(kernel);
+  rspcl_ctx::ProfAcc a;
+  if (it != ctx->prof_acc.end()) a = it->second;
+  if (total_ms) *total_ms = a.ms;
+  if (launches) *launches = a.launches;
+  if (units) *units = a.units;
+  return RSPCL_OK;
+}
+
 extern "C" int rspcl_host_alloc(rspcl_ctx* ctx, size_t bytes, void** out) {
   CU(ctx, cudaMallocHost(out, bytes ? bytes : 1));
   return RSPCL_OK;
@@ -207,6 +248,7 @@ extern "C" int rspcl_cloud_upload(rspcl_ctx* ctx, rspcl_cloud* c, const void* ho
   if (total > 0) {
     CU(ctx, cudaMemcpyAsync(raw, host, (size_t)total * esz, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid(blocks_per_seg(ctx, n_seg, maxc, 256), n_seg);
+    ProfScope prof(ctx, "k_unpack", (double)total);
     if (layout == RSPCL_LAYOUT_PCL32)
       k_unpack<true><<<grid, 256, 0, ctx->stream>>>(raw, d_off, c->count, c->pts, c->gray, c->stride);
     else

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <map>
 #include "../../include/rspcl.h"
 
 struct rspcl_ctx {
@@ -18,6 +19,39 @@ struct rspcl_ctx {
   // grow-only pinned staging buffer for small result read-backs
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
+  // optional per-kernel event profile
+  bool prof_on = false;
+  struct ProfRec { cudaEvent_t a, b; int kernel; double units; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<std::string> prof_names;
+  struct ProfAcc { double ms = 0; long long launches = 0; double units = 0; };
+  std::map<std::string, ProfAcc> prof_acc;
+};
+
+// RAII bracket: records an event pair around the launches issued while it is alive (only when profiling is on)
+struct ProfScope {
+  rspcl_ctx* ctx;
+  int slot = -1;
+  ProfScope(rspcl_ctx* c, const char* name, double units) : ctx(c) {
+    if (!c->prof_on) return;
+    rspcl_ctx::ProfRec r;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    int k = -1;
+    for (size_t i = 0; i < c->prof_names.size(); ++i)
+      if (c->prof_names[i] == name) k = (int)i;
+    if (k < 0) {
+      c->prof_names.push_back(name);
+      k = (int)c->prof_names.size() - 1;
+    }
+    r.kernel = k;
+    r.units = units;
+    cudaEventRecord(r.a, c->stream);
+    c->prof_recs.push_back(r);
+    slot = (int)c->prof_recs.size() - 1;
+  }
+  ~ProfScope() {
+    if (slot >= 0) cudaEventRecord(ctx->prof_recs[slot].b, ctx->stream);
+  }
 };
 
 struct rspcl_cloud {

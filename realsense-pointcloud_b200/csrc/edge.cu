@@ -323,9 +323,13 @@ extern "C" int rspcl_edge_extract(rspcl_ctx* ctx, const rspcl_cloud* frames, flo
   CU(ctx, cudaMemsetAsync(d_over, 0, sizeof(int), ctx->stream));
 
   dim3 g1(div_up(w, TW), div_up(h, TH), S);
-  k_canny_nms<<<g1, dim3(64, 4), 0, ctx->stream>>>(frames->gray, w, h, stride, t_low, t_high, cls, parent);
-  LAUNCH_CHECK(ctx);
+  {
+    ProfScope prof(ctx, "k_canny_nms", (double)S * n);
+    k_canny_nms<<<g1, dim3(64, 4), 0, ctx->stream>>>(frames->gray, w, h, stride, t_low, t_high, cls, parent);
+    LAUNCH_CHECK(ctx);
+  }
   dim3 g2(blocks_per_seg(ctx, S, n, 256), S);
+  ProfScope prof_h(ctx, "edge_hysteresis_compact", (double)S * n);
   k_uf_merge<<<g2, 256, 0, ctx->stream>>>(cls, parent, w, h, stride);
   LAUNCH_CHECK(ctx);
   k_uf_flag<<<g2, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);

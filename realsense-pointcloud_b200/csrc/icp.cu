@@ -436,6 +436,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   DevGrid g;
   g.shared_target = shared_target;
   if (!brute) {
+    ProfScope prof(ctx, "grid_build", (double)S * tgt->max_count_hint);
     int rc = grid_build(ctx, tgt, cs, &g, d_range);
     if (rc) return rc;
   }
@@ -444,9 +445,18 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   // between chunks (1, 1, 2, 4, 8, ... iterations), so the reference's one-iteration aligns cost one read-back.
   dim3 gstep(nblk, S);
   int done_iters = 0, chunk = 1, active = S;
+  double prof_units = 0;  // source points per launch (all pairs; converged pairs exit early)
+  if (ctx->prof_on) {
+    std::vector<int> c(S);
+    CU(ctx, cudaMemcpyAsync(c.data(), src->count, S * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int v : c) prof_units += v;
+  }
   while (done_iters < prm->max_iterations && active > 0) {
     const int todo = (chunk < prm->max_iterations - done_iters) ? chunk : prm->max_iterations - done_iters;
     for (int k = 0; k < todo; ++k) {
+      {
+      ProfScope prof(ctx, "k_icp_step", prof_units);
       if (brute)
         k_icp_step<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count, tgt->stride,
                                                        partials, d_first_corr);
@@ -454,6 +464,8 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         k_icp_step<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count, tgt->stride,
                                                         partials, d_first_corr);
       LAUNCH_CHECK(ctx);
+      }
+      ProfScope prof2(ctx, "k_icp_solve", (double)S);
       k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, partials, nblk, dp, n_active);
       LAUNCH_CHECK(ctx);
     }

@@ -906,7 +906,11 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   CU(ctx, cudaMemsetAsync(d_range, 0, sizeof(int), ctx->stream));
   NdtGridDev G;
   G.shared_target = shared_target;
-  int rc = ndt_grid_build(ctx, tgt, prm, &G, d_range);
+  int rc;
+  {
+    ProfScope prof(ctx, "ndt_voxel_build", (double)tgt->n_seg * tgt->max_count_hint);
+    rc = ndt_grid_build(ctx, tgt, prm, &G, d_range);
+  }
   if (rc) return rc;
 
   NdtState* st = nullptr;
@@ -934,8 +938,11 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   dim3 ge(nblk, S);
   while (active > 0 && done_evals < max_evals) {
     for (int k = 0; k < chunk; ++k) {
-      k_ndt_eval<<<ge, NT, 0, ctx->stream>>>(src->pts, src->count, src->stride, ev, G, d1, d2, partials);
-      LAUNCH_CHECK(ctx);
+      {
+        ProfScope prof(ctx, "k_ndt_eval", (double)S * src->max_count_hint);
+        k_ndt_eval<<<ge, NT, 0, ctx->stream>>>(src->pts, src->count, src->stride, ev, G, d1, d2, partials);
+        LAUNCH_CHECK(ctx);
+      }
       k_ndt_control<<<S, 32, 0, ctx->stream>>>(st, ev, partials, nblk, ctl, n_active);
       LAUNCH_CHECK(ctx);
     }

@@ -175,6 +175,7 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
     CU(ctx, cudaMemcpyAsync(d_T, hT.data(), hT.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(d_acc, accept.data(), n_pairs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     dim3 gt(blocks_per_seg(ctx, n_pairs, npx, 256), n_pairs);
+    ProfScope prof(ctx, "k_transform2", (double)n_pairs * npx);
     k_transform2_gather<<<gt, 256, 0, ctx->stream>>>(frames->pts, npx, frames->stride, d_src, d_T, d_T + (size_t)n_pairs * 16,
                                                      d_acc, out_transformed->pts, out_transformed->count,
                                                      out_transformed->stride);

@@ -253,6 +253,7 @@ int voxel_approx_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float leaf[
     obuf = tmp;
     ostride = in->stride;
   }
+  ProfScope prof(ctx, "k_approx_voxel", (double)S * in->max_count_hint);
   k_approx_voxel<<<S, VT, VOX_SMEM, ctx->stream>>>(in->pts, in->count, in->stride, inv, sorted, ev, obuf, out->count, ostride,
                                                    d_over);
   LAUNCH_CHECK(ctx);

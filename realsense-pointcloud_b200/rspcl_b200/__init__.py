@@ -60,7 +60,7 @@ NDT_VOXEL = np.dtype([("ijk", "<i4", 3), ("npts", "<i4"), ("centroid", "<f4", 3)
 
 EXPORTS = [
     "rspcl_ctx_create", "rspcl_ctx_destroy", "rspcl_last_error", "rspcl_ctx_sync", "rspcl_timer_start",
-    "rspcl_timer_stop", "rspcl_launch_count", "rspcl_host_alloc", "rspcl_host_free", "rspcl_cloud_create",
+    "rspcl_timer_stop", "rspcl_launch_count", "rspcl_profile_enable", "rspcl_profile_reset", "rspcl_profile_get", "rspcl_host_alloc", "rspcl_host_free", "rspcl_cloud_create",
     "rspcl_cloud_destroy", "rspcl_cloud_n_seg", "rspcl_cloud_stride", "rspcl_cloud_dims", "rspcl_cloud_upload",
     "rspcl_cloud_counts", "rspcl_cloud_download", "rspcl_crop35", "rspcl_edge_extract", "rspcl_voxel_approx",
     "rspcl_voxel_keys", "rspcl_transform", "rspcl_concat", "rspcl_cloud_copy_segment", "rspcl_icp_reference_params",
@@ -180,6 +180,17 @@ class Context:
 
     def launches(self):
         return lib().rspcl_launch_count(self.h)
+
+    def profile(self, on):
+        self.check(lib().rspcl_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self.check(lib().rspcl_profile_reset(self.h))
+
+    def profile_get(self, kernel):
+        ms, n, u = C.c_double(), C.c_longlong(), C.c_double()
+        self.check(lib().rspcl_profile_get(self.h, kernel.encode(), C.byref(ms), C.byref(n), C.byref(u)))
+        return {"ms": ms.value, "launches": n.value, "units": u.value}
 
     def pinned(self, nbytes):
         """numpy uint8 view of a pinned host allocation (kept alive by the returned array's base)."""
