@@ -7,10 +7,25 @@
 
 namespace {
 
-__global__ void k_grid_init(unsigned long long* __restrict__ keys, int* __restrict__ cnt, unsigned cap) {
+__global__ void k_grid_init(GridSlot* __restrict__ slots, int* __restrict__ cnt, unsigned cap) {
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-    keys[i] = GRID_EMPTY;
+    GridSlot e;
+    e.key = GRID_EMPTY;
+    e.start = 0;
+    e.cnt = 0;
+    slots[i] = e;
     cnt[i] = 0;
+  }
+}
+
+__global__ void k_grid_finalize(GridSlot* __restrict__ slots, const int* __restrict__ cnt, const int* __restrict__ start,
+                                unsigned cap) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    const int c = cnt[i];
+    if (c) {
+      slots[i].start = start[i];
+      slots[i].cnt = c;
+    }
   }
 }
 
@@ -30,9 +45,9 @@ __global__ void k_grid_insert(const float4* __restrict__ pts, const int* __restr
         atomicExch(range_flag, 1);
       } else {
         const unsigned long long key = grid_key(seg, ix, iy, iz);
-        unsigned s = grid_hash(key) & g.cap_mask;
+        unsigned s = grid_hash4(seg, ix, iy, iz) & g.cap_mask;
         while (true) {
-          unsigned long long prev = atomicCAS(&g.keys[s], GRID_EMPTY, key);
+          unsigned long long prev = atomicCAS(&g.slots[s].key, GRID_EMPTY, key);
           if (prev == GRID_EMPTY || prev == key) break;
           s = (s + 1) & g.cap_mask;
         }
@@ -172,7 +187,7 @@ int grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, float cell_size, DevGrid*
   g->cs = cell_size;
   g->inv_cs = 1.0f / cell_size;
   g->n_total = n_total;
-  CU(ctx, scratch_alloc(ctx, &g->keys, (size_t)cap));
+  CU(ctx, scratch_alloc(ctx, &g->slots, (size_t)cap));
   CU(ctx, scratch_alloc(ctx, &g->cnt, (size_t)cap));
   CU(ctx, scratch_alloc(ctx, &g->start, (size_t)cap));
   CU(ctx, scratch_alloc(ctx, &g->sorted, (size_t)n_total));
@@ -180,7 +195,7 @@ int grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, float cell_size, DevGrid*
   CU(ctx, scratch_alloc(ctx, &g->rank_of, (size_t)n_total));
   int* seg_off = nullptr;
   CU(ctx, scratch_alloc(ctx, &seg_off, (size_t)S));
-  k_grid_init<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(g->keys, g->cnt, cap);
+  k_grid_init<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(g->slots, g->cnt, cap);
   LAUNCH_CHECK(ctx);
   k_seg_offsets<<<div_up(S, 256), 256, 0, ctx->stream>>>(tgt->count, S, tgt->stride, seg_off);
   LAUNCH_CHECK(ctx);
@@ -191,20 +206,21 @@ int grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, float cell_size, DevGrid*
   if (rc) return rc;
   k_grid_scatter<<<grid, 256, 0, ctx->stream>>>(tgt->pts, tgt->count, tgt->stride, *g, seg_off);
   LAUNCH_CHECK(ctx);
+  k_grid_finalize<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(g->slots, g->cnt, g->start, cap);
+  LAUNCH_CHECK(ctx);
   scratch_free(ctx, seg_off);
   scratch_free(ctx, g->slot_of);
   scratch_free(ctx, g->rank_of);
-  g->slot_of = g->rank_of = nullptr;
+  scratch_free(ctx, g->cnt);
+  scratch_free(ctx, g->start);
+  g->slot_of = g->rank_of = g->cnt = g->start = nullptr;
   return RSPCL_OK;
 }
 
 void grid_free(rspcl_ctx* ctx, DevGrid* g) {
-  scratch_free(ctx, g->keys);
-  scratch_free(ctx, g->cnt);
-  scratch_free(ctx, g->start);
+  scratch_free(ctx, g->slots);
   scratch_free(ctx, g->sorted);
-  g->keys = nullptr;
-  g->cnt = g->start = nullptr;
+  g->slots = nullptr;
   g->sorted = nullptr;
 }
 

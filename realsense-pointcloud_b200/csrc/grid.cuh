@@ -2,23 +2,31 @@
 //
 // Replaces the FLANN kd-tree PCL builds inside Registration::align (initCompute) for every setInputTarget
 // (icp:79,109; ndt:72,97; incr:58).  A target batch is binned into cubic cells; occupied cells live in one
-// open-addressing hash table keyed by (segment, ix, iy, iz) and point at a contiguous slice of a cell-sorted copy of
-// the target points (counting sort by hash slot: count -> exclusive scan -> scatter).
+// open-addressing hash table keyed by (segment, ix, iy, iz).  A slot is 16 bytes {key, start, count} so that one
+// 128-bit load resolves a probe, and points at a contiguous slice of a cell-sorted copy of the target points
+// (counting sort by hash slot: count -> exclusive scan -> scatter).
 #pragma once
 #include "common.cuh"
 
+struct __align__(16) GridSlot {
+  unsigned long long key;  // cell key or GRID_EMPTY
+  int start;               // first index into sorted
+  int cnt;                 // points in the cell
+};
+
 struct DevGrid {
-  unsigned long long* keys = nullptr;  // [cap] cell key or EMPTY
-  int* cnt = nullptr;                  // [cap] points in the cell
-  int* start = nullptr;                // [cap] first index into sorted
-  float4* sorted = nullptr;            // [n_total] {x,y,z, original index within its segment (int bits)}
+  GridSlot* slots = nullptr;  // [cap]
+  float4* sorted = nullptr;   // [n_total] {x,y,z, original index within its segment (int bits)}
   unsigned cap_mask = 0;
   float inv_cs = 0.f;  // 1 / cell size
   float cs = 0.f;
   int shared_target = 0;  // 1: all queries use segment 0 of the target
   long long n_total = 0;
-  int* slot_of = nullptr;  // [n_total] scratch (slot, rank) per target point
-  int* rank_of = nullptr;
+  // build-time scratch
+  int* cnt = nullptr;      // [cap]
+  int* start = nullptr;    // [cap]
+  int* slot_of = nullptr;  // [n_total]
+  int* rank_of = nullptr;  // [n_total]
 };
 
 #define GRID_EMPTY 0xFFFFFFFFFFFFFFFFull
@@ -30,6 +38,15 @@ __device__ __forceinline__ unsigned long long grid_key(int seg, int ix, int iy, 
 __device__ __forceinline__ bool grid_in_range(int ix, int iy, int iz) {
   return ix > -32768 && ix < 32767 && iy > -32768 && iy < 32767 && iz > -32768 && iz < 32767;
 }
+// 32-bit multiplicative hash of the cell coordinates (a handful of IMADs; the 64-bit key is what is compared)
+__device__ __forceinline__ unsigned grid_hash4(int seg, int ix, int iy, int iz) {
+  unsigned h = (unsigned)ix * 0x9E3779B1u ^ (unsigned)iy * 0x85EBCA77u ^ (unsigned)iz * 0xC2B2AE3Du ^ (unsigned)seg * 0x27D4EB2Fu;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return h;
+}
+// generic 64-bit mix (NDT voxel table)
 __device__ __forceinline__ unsigned grid_hash(unsigned long long k) {
   k ^= k >> 33;
   k *= 0xff51afd7ed558ccdull;
@@ -40,19 +57,31 @@ __device__ __forceinline__ unsigned grid_hash(unsigned long long k) {
 }
 __device__ __forceinline__ int grid_cell(float v, float inv_cs) { return __float2int_rd(__fmul_rn(v, inv_cs)); }
 
-// slot of an occupied cell or -1
-__device__ __forceinline__ int grid_lookup(const DevGrid& g, unsigned long long key) {
-  unsigned s = grid_hash(key) & g.cap_mask;
+__device__ __forceinline__ GridSlot grid_load_slot(const GridSlot* p) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  GridSlot s;
+  s.key = ((unsigned long long)v.y << 32) | v.x;
+  s.start = (int)v.z;
+  s.cnt = (int)v.w;
+  return s;
+}
+
+// resolve a probe that did not hit on its first slot (rare: linear probing)
+static __device__ __noinline__ GridSlot grid_probe_slow(const DevGrid& g, unsigned long long key, unsigned s) {
   while (true) {
-    unsigned long long k = __ldg(&g.keys[s]);
-    if (k == key) return (int)s;
-    if (k == GRID_EMPTY) return -1;
     s = (s + 1) & g.cap_mask;
+    GridSlot sl = grid_load_slot(&g.slots[s]);
+    if (sl.key == key) return sl;
+    if (sl.key == GRID_EMPTY) {
+      sl.cnt = 0;
+      return sl;
+    }
   }
 }
 
-// Exact nearest neighbour among target points within `r` of q (r <= ~cs/2): scans the <= 2x2x2 cells that the ball
-// touches.  Squared distance in FLANN L2_Simple order, ties -> lowest original index.  Returns -1 if none.
+// Exact nearest neighbour among target points within `r` of q: scans the <= 2x2x2 cells that the ball touches
+// (cell size >= 2r).  All eight first-probe loads are issued before any is consumed (memory-level parallelism);
+// squared distance in FLANN L2_Simple order; ties -> lowest original index.  Returns -1 if none.
 __device__ __forceinline__ int grid_nn_bounded(const DevGrid& g, int seg, float qx, float qy, float qz, float r,
                                                float* out_d2, float4* out_pt) {
   const int x0 = grid_cell(qx - r, g.inv_cs), x1 = grid_cell(qx + r, g.inv_cs);
@@ -66,23 +95,40 @@ __device__ __forceinline__ int grid_nn_bounded(const DevGrid& g, int seg, float 
     return -1;
   }
   const int tseg = g.shared_target ? 0 : seg;
-  for (int iz = z0; iz <= z1; ++iz)
-    for (int iy = y0; iy <= y1; ++iy)
-      for (int ix = x0; ix <= x1; ++ix) {
-        const int s = grid_lookup(g, grid_key(tseg, ix, iy, iz));
-        if (s < 0) continue;
-        const int b = __ldg(&g.start[s]), e = b + __ldg(&g.cnt[s]);
-        for (int k = b; k < e; ++k) {
-          const float4 t = __ldg(&g.sorted[k]);
-          const float d = dist2_l2simple(qx, qy, qz, t.x, t.y, t.z);
-          const int idx = __float_as_int(t.w);
-          if (d < bd || (d == bd && idx < best)) {
-            bd = d;
-            best = idx;
-            bp = t;
-          }
-        }
+  GridSlot sl[8];
+  unsigned long long keys[8];
+  unsigned hs[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    // duplicate cells (when the ball does not straddle a cell face) are marked by an impossible key
+    const bool dup = ((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0);
+    const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
+    keys[c] = dup ? GRID_EMPTY : grid_key(tseg, ix, iy, iz);
+    hs[c] = grid_hash4(tseg, ix, iy, iz) & g.cap_mask;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) sl[c] = grid_load_slot(&g.slots[hs[c]]);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (keys[c] == GRID_EMPTY) continue;
+    GridSlot s = sl[c];
+    if (s.key != keys[c]) {
+      if (s.key == GRID_EMPTY) continue;
+      s = grid_probe_slow(g, keys[c], hs[c]);
+      if (s.cnt == 0) continue;
+    }
+    const int e = s.start + s.cnt;
+    for (int k = s.start; k < e; ++k) {
+      const float4 t = __ldg(&g.sorted[k]);
+      const float d = dist2_l2simple(qx, qy, qz, t.x, t.y, t.z);
+      const int idx = __float_as_int(t.w);
+      if (d < bd || (d == bd && idx < best)) {
+        bd = d;
+        best = idx;
+        bp = t;
       }
+    }
+  }
   *out_d2 = bd;
   if (out_pt) *out_pt = bp;
   return best;

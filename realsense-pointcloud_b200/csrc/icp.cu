@@ -8,7 +8,8 @@
 //                    voxel-hash grid (<= 2x2x2 cells), reject beyond max_corr_dist, and reduce
 //                    {n, sum s, sum t, sum s t^T, sum d^2} (17 fp64) per CTA with warp shuffles.  No atomics: CTA
 //                    partials are combined in a fixed order so results are reproducible run to run.
-//   K5b k_icp_solve  one warp per pair: combine partials, Umeyama (3x3 Jacobi SVD, fp64), final = T * final,
+//   K5b k_icp_solve  one warp per pair: combine the partials in block order, Umeyama (fp64 polar decomposition by
+//                    scaled Newton; Jacobi SVD fallback for degenerate / reflected covariances), final = T * final,
 //                    DefaultConvergenceCriteria.
 // Algorithmic bytes per source point per iteration: 16 R (source) + 16 R (matched target) = 32 B; the
 // in-place update of the working cloud (16 W) and the neighbour-cell probes are overhead on top of that.
@@ -46,6 +47,10 @@ struct IcpDevParams {
 __device__ __forceinline__ void mat4_identity(float* T) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+}
+
+__device__ __forceinline__ double det3(const double* M) {
+  return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
 }
 
 // ---- 3x3 one-sided Jacobi SVD in fp64: A = U diag(s) V^T, s descending (row-major)
@@ -130,8 +135,45 @@ __device__ void svd3(const double* A_in, double* U, double* s, double* V) {
   }
 }
 
-__device__ __forceinline__ double det3(const double* M) {
-  return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+// Orthogonal polar factor of a well-conditioned 3x3 with positive determinant by scaled Newton iteration
+// (X <- (g X + X^-T / g) / 2).  For det(sigma) > 0 it equals U V^T of the SVD, i.e. Umeyama's rotation with S = I,
+// at a fraction of the latency of a Jacobi SVD on one thread.  Returns false if the matrix is too close to singular
+// (or a reflection is needed) and the SVD path must decide.
+__device__ bool polar_rotation(const double* A, double* R) {
+  double X[9];
+  double fro2 = 0;
+  for (int i = 0; i < 9; ++i) {
+    X[i] = A[i];
+    fro2 += A[i] * A[i];
+  }
+  const double det0 = det3(A);
+  const double scale = sqrt(fro2 / 3.0);
+  if (!(det0 > 1e-7 * scale * scale * scale)) return false;
+  for (int it = 0; it < 32; ++it) {
+    const double c[9] = {X[4] * X[8] - X[5] * X[7], X[5] * X[6] - X[3] * X[8], X[3] * X[7] - X[4] * X[6],
+                         X[2] * X[7] - X[1] * X[8], X[0] * X[8] - X[2] * X[6], X[1] * X[6] - X[0] * X[7],
+                         X[1] * X[5] - X[2] * X[4], X[2] * X[3] - X[0] * X[5], X[0] * X[4] - X[1] * X[3]};
+    const double det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
+    if (!(det > 0.0)) return false;
+    const double idet = 1.0 / det;
+    double nx = 0, ny = 0;
+    for (int i = 0; i < 9; ++i) {
+      nx += X[i] * X[i];
+      ny += c[i] * c[i];
+    }
+    ny *= idet * idet;  // ||X^-T||_F^2 (c is the cofactor matrix = det * X^-T)
+    const double g = sqrt(sqrt(ny / nx));
+    double diff = 0, nn = 0;
+    for (int i = 0; i < 9; ++i) {
+      const double v = 0.5 * (g * X[i] + c[i] * idet / g);
+      diff += (v - X[i]) * (v - X[i]);
+      nn += v * v;
+      X[i] = v;
+    }
+    if (diff <= 1e-30 * nn) break;
+  }
+  for (int i = 0; i < 9; ++i) R[i] = X[i];
+  return true;
 }
 
 // pcl::umeyama(src, dst, with_scaling=false) from raw fp64 moments: S = {n, sum s, sum t, sum s_r t_c}
@@ -142,17 +184,19 @@ __device__ void umeyama_from_moments(const double* S, float* T) {
   double sigma[9];  // sigma(r,c) = mean((t_r - mt_r)(s_c - ms_c))
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) sigma[r * 3 + c] = S[7 + c * 3 + r] * inv_n - mt[r] * ms[c];
-  double U[9], sv[3], V[9];
-  svd3(sigma, U, sv, V);
-  const double d = det3(U) * det3(V);
-  const double Sd[3] = {1.0, 1.0, d < 0 ? -1.0 : 1.0};
   double R[9];
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) {
-      double acc = 0;
-      for (int k = 0; k < 3; ++k) acc += U[r * 3 + k] * Sd[k] * V[c * 3 + k];
-      R[r * 3 + c] = acc;
-    }
+  if (!polar_rotation(sigma, R)) {
+    double U[9], sv[3], V[9];
+    svd3(sigma, U, sv, V);
+    const double d = det3(U) * det3(V);
+    const double Sd[3] = {1.0, 1.0, d < 0 ? -1.0 : 1.0};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double acc = 0;
+        for (int k = 0; k < 3; ++k) acc += U[r * 3 + k] * Sd[k] * V[c * 3 + k];
+        R[r * 3 + c] = acc;
+      }
+  }
   mat4_identity(T);
   for (int r = 0; r < 3; ++r) {
     for (int c = 0; c < 3; ++c) T[c * 4 + r] = (float)R[r * 3 + c];
@@ -198,6 +242,60 @@ __global__ void k_icp_init(IcpState* __restrict__ st, const float* __restrict__ 
   S.n_corr = 0;
   S.pad[0] = S.pad[1] = 0;
   st[s] = S;
+}
+
+// Umeyama + DefaultConvergenceCriteria for one pair (one thread), given the 17 combined sums
+__device__ void icp_solve_pair(IcpState* S, const double* sums, const IcpDevParams& prm, int* n_active) {
+  S->apply_inc = 0;
+  const int n_corr = (int)(sums[0] + 0.5);
+  S->n_corr = n_corr;
+  if (n_corr < prm.min_corr) {
+    // icp.hpp: "Not enough correspondences found" -> NO_CORRESPONDENCES, converged_ = false, loop exits
+    S->state = RSPCL_CONV_NO_CORRESPONDENCES;
+    S->converged = 0;
+    S->done = 1;
+    atomicSub(n_active, 1);
+    return;
+  }
+  float T[16];
+  umeyama_from_moments(sums, T);
+  for (int i = 0; i < 16; ++i) S->inc_T[i] = T[i];
+  S->apply_inc = 1;
+  mat4_mul(T, S->final_T, S->final_T);
+  const int it = ++S->iterations;
+  const double mse = sums[16] / (double)n_corr;
+  S->mse = mse;
+  // DefaultConvergenceCriteria::hasConverged
+  int state = RSPCL_CONV_NOT_CONVERGED;
+  bool conv = false;
+  if (it >= prm.max_iterations) {
+    state = RSPCL_CONV_ITERATIONS;
+    conv = true;
+  } else {
+    const double cos_angle = 0.5 * (double)(fadd(fadd(fadd(T[0], T[5]), T[10]), -1.0f));
+    const double tr2 = (double)fadd(fadd(fmul(T[12], T[12]), fmul(T[13], T[13])), fmul(T[14], T[14]));
+    if (cos_angle >= prm.rot_thr && tr2 <= prm.trans_thr) {
+      state = RSPCL_CONV_TRANSFORM;
+      conv = true;
+    } else {
+      const double prev = S->prev_mse;
+      if (fabs(mse - prev) < prm.mse_abs) {
+        state = RSPCL_CONV_ABS_MSE;
+        conv = true;
+      } else if (fabs(mse - prev) / prev < prm.mse_rel) {
+        state = RSPCL_CONV_REL_MSE;
+        conv = true;
+      } else {
+        S->prev_mse = mse;
+      }
+    }
+  }
+  S->state = state;
+  if (conv) {
+    S->converged = 1;
+    S->done = 1;
+    atomicSub(n_active, 1);
+  }
 }
 
 template <bool BRUTE>
@@ -286,70 +384,21 @@ __global__ void __launch_bounds__(IT) k_icp_step(float4* __restrict__ work, cons
   }
 }
 
+// K5b: one warp per pair combines the CTA partials in block order (deterministic) and runs the solve
 __global__ void __launch_bounds__(32) k_icp_solve(IcpState* __restrict__ st, const double* __restrict__ partials, int nblk,
                                                   IcpDevParams prm, int* __restrict__ n_active) {
   const int seg = blockIdx.x;
-  IcpState* S = &st[seg];
-  if (S->done) return;
+  if (st[seg].done) return;
   const int lane = threadIdx.x;
-  // combine CTA partials: lane k sums quantity k over the blocks in ascending order (fixed order -> deterministic)
-  double v = 0;
-  if (lane < NRED)
-    for (int b = 0; b < nblk; ++b) v += partials[((size_t)seg * nblk + b) * NRED + lane];
   __shared__ double sums[NRED];
-  if (lane < NRED) sums[lane] = v;
+  if (lane < NRED) {
+    double v = 0;
+    const double* P = partials + (size_t)seg * nblk * NRED + lane;
+    for (int b = 0; b < nblk; ++b) v += P[(size_t)b * NRED];
+    sums[lane] = v;
+  }
   __syncwarp();
-  if (lane != 0) return;
-  S->apply_inc = 0;
-  const int n_corr = (int)(sums[0] + 0.5);
-  S->n_corr = n_corr;
-  if (n_corr < prm.min_corr) {
-    // icp.hpp: "Not enough correspondences found" -> NO_CORRESPONDENCES, converged_ = false, loop exits
-    S->state = RSPCL_CONV_NO_CORRESPONDENCES;
-    S->converged = 0;
-    S->done = 1;
-    atomicSub(n_active, 1);
-    return;
-  }
-  float T[16];
-  umeyama_from_moments(sums, T);
-  for (int i = 0; i < 16; ++i) S->inc_T[i] = T[i];
-  S->apply_inc = 1;
-  mat4_mul(T, S->final_T, S->final_T);
-  const int it = ++S->iterations;
-  const double mse = sums[16] / (double)n_corr;
-  S->mse = mse;
-  // DefaultConvergenceCriteria::hasConverged
-  int state = RSPCL_CONV_NOT_CONVERGED;
-  bool conv = false;
-  if (it >= prm.max_iterations) {
-    state = RSPCL_CONV_ITERATIONS;
-    conv = true;
-  } else {
-    const double cos_angle = 0.5 * (double)(fadd(fadd(fadd(T[0], T[5]), T[10]), -1.0f));
-    const double tr2 = (double)fadd(fadd(fmul(T[12], T[12]), fmul(T[13], T[13])), fmul(T[14], T[14]));
-    if (cos_angle >= prm.rot_thr && tr2 <= prm.trans_thr) {
-      state = RSPCL_CONV_TRANSFORM;
-      conv = true;
-    } else {
-      const double prev = S->prev_mse;
-      if (fabs(mse - prev) < prm.mse_abs) {
-        state = RSPCL_CONV_ABS_MSE;
-        conv = true;
-      } else if (fabs(mse - prev) / prev < prm.mse_rel) {
-        state = RSPCL_CONV_REL_MSE;
-        conv = true;
-      } else {
-        S->prev_mse = mse;
-      }
-    }
-  }
-  S->state = state;
-  if (conv) {
-    S->converged = 1;
-    S->done = 1;
-    atomicSub(n_active, 1);
-  }
+  if (lane == 0) icp_solve_pair(&st[seg], sums, prm, n_active);
 }
 
 __global__ void k_copy_work(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
@@ -456,14 +505,14 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     const int todo = (chunk < prm->max_iterations - done_iters) ? chunk : prm->max_iterations - done_iters;
     for (int k = 0; k < todo; ++k) {
       {
-      ProfScope prof(ctx, "k_icp_step", prof_units);
-      if (brute)
-        k_icp_step<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count, tgt->stride,
-                                                       partials, d_first_corr);
-      else
-        k_icp_step<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count, tgt->stride,
-                                                        partials, d_first_corr);
-      LAUNCH_CHECK(ctx);
+        ProfScope prof(ctx, "k_icp_step", prof_units);
+        if (brute)
+          k_icp_step<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count,
+                                                         tgt->stride, partials, d_first_corr);
+        else
+          k_icp_step<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count,
+                                                          tgt->stride, partials, d_first_corr);
+        LAUNCH_CHECK(ctx);
       }
       ProfScope prof2(ctx, "k_icp_solve", (double)S);
       k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, partials, nblk, dp, n_active);

@@ -1,0 +1,88 @@
+// rs_pcl_b200 -- headless counterpart of the reference CLI's registration modes (main.cpp:185-237), on the B200 path.
+//
+//   rs_pcl_b200 [--dataset DIR] [--scheme ndt|icp|incremental] --registration <prefix> [deg] <N>
+//       loads DIR/<prefix>-<i>.pcd (i < N), runs the scheme (default: NDT edge-based, like main.cpp:208,218), writes
+//       DIR/<prefix>-registration (main.cpp:87, no suffix) and prints the per-frame transforms as one JSON line.
+//   rs_pcl_b200 [--dataset DIR] --edges <file>
+//       extract_edge_features of DIR/<file> (main.cpp:58-62); prints the edge count, writes DIR/<file>.edges.pcd.
+// The GL viewer loops of the reference (main.cpp:65-73,90-98) and the capture modes are out of scope.
+#include <cstdlib>
+#include <cstring>
+#include "rspcl.hpp"
+
+static void print_json(const std::vector<rspcl::Matrix4f>& T, const std::vector<int>& acc, size_t npts) {
+  std::printf("{\"points\": %zu, \"accepted\": [", npts);
+  for (size_t i = 0; i < acc.size(); ++i) std::printf("%s%d", i ? ", " : "", acc[i]);
+  std::printf("], \"transforms\": [");
+  for (size_t k = 0; k < T.size(); ++k) {
+    std::printf("%s[", k ? ", " : "");
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) std::printf("%s%.9g", (r || c) ? ", " : "", T[k](r, c));  // row-major rows
+    std::printf("]");
+  }
+  std::printf("]}\n");
+}
+
+int main(int argc, char** argv) {
+  try {
+    std::string dir = "dataset", scheme = "ndt";
+    std::vector<std::string> a;
+    for (int i = 1; i < argc; ++i) {
+      if (!std::strcmp(argv[i], "--dataset") && i + 1 < argc) dir = argv[++i];
+      else if (!std::strcmp(argv[i], "--scheme") && i + 1 < argc) scheme = argv[++i];
+      else a.push_back(argv[i]);
+    }
+    if (a.size() >= 2 && a[0] == "--edges") {
+      rgb_point_cloud_pointer c(new rgb_point_cloud);
+      rspcl::io::loadPCDFile(dir + "/" + a[1], *c);
+      auto e = rspcl::extract_edge_features(c);
+      rspcl::io::savePCDFileBinary(dir + "/" + a[1] + ".edges.pcd", *e);
+      std::printf("{\"edge_points\": %zu}\n", e->size());
+      return 0;
+    }
+    if (a.size() >= 3 && a[0] == "--registration") {
+      const std::string prefix = a[1];
+      float rads = -0.523599f;
+      int frames;
+      if (a.size() == 3) {
+        frames = std::atoi(a[2].c_str());
+      } else {
+        const double deg = std::atof(a[2].c_str());
+        rads = static_cast<float>((deg / 180.0) * M_PI);  // main.cpp:214-215
+        frames = std::atoi(a[3].c_str());
+      }
+      std::vector<rgb_point_cloud_pointer> clouds;
+      for (int i = 0; i < frames; ++i) {
+        rgb_point_cloud_pointer c(new rgb_point_cloud);
+        rspcl::io::loadPCDFile(dir + "/" + prefix + "-" + std::to_string(i) + ".pcd", *c);
+        clouds.push_back(c);
+      }
+      rgb_point_cloud_pointer result;
+      std::vector<rspcl::Matrix4f> T;
+      std::vector<int> acc;
+      if (scheme == "incremental") {
+        IncrementalICP s;
+        result = s.registration(clouds);
+        T = s.transforms;
+        acc.assign(T.size(), 1);
+      } else if (scheme == "icp") {
+        ICPEdgeBasedRegistration s(rads);
+        result = s.registration(clouds);
+        T = s.transforms, acc = s.accepted;
+      } else {
+        NDTEdgeBasedRegistration s(rads);
+        result = s.registration(clouds);
+        T = s.transforms, acc = s.accepted;
+      }
+      rspcl::io::savePCDFileBinary(dir + "/" + prefix + "-registration", *result);
+      print_json(T, acc, result->size());
+      return 0;
+    }
+    std::fprintf(stderr, "usage: rs_pcl_b200 [--dataset DIR] [--scheme ndt|icp|incremental] --registration <prefix> [deg] <N>\n"
+                         "       rs_pcl_b200 [--dataset DIR] --edges <file>\n");
+    return 2;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "rs_pcl_b200: %s\n", e.what());
+    return 1;
+  }
+}
