@@ -322,7 +322,7 @@ def main():
     step()
     ms_prof = ctx.timer_stop()
     ctx.profile(False)
-    kern = {k: ctx.profile_get(k) for k in ("k_icp_step", "k_icp_solve", "grid_build", "k_canny_nms",
+    kern = {k: ctx.profile_get(k) for k in ("k_icp_persist", "k_icp_step", "k_icp_solve", "grid_build", "k_canny_nms",
                                             "edge_hysteresis_compact", "k_approx_voxel", "k_transform2", "k_ndt_eval",
                                             "ndt_voxel_build")}
     ki = kern["k_icp_step"]

@@ -49,9 +49,15 @@ struct ProfScope {
     c->prof_recs.push_back(r);
     slot = (int)c->prof_recs.size() - 1;
   }
-  ~ProfScope() {
-    if (slot >= 0) cudaEventRecord(ctx->prof_recs[slot].b, ctx->stream);
+  void set_units(double u) {
+    if (slot >= 0) ctx->prof_recs[slot].units = u;
   }
+  void end() {
+    if (slot >= 0 && !ended) cudaEventRecord(ctx->prof_recs[slot].b, ctx->stream);
+    ended = true;
+  }
+  bool ended = false;
+  ~ProfScope() { end(); }
 };
 
 struct rspcl_cloud {

@@ -16,8 +16,12 @@
 // The "unbounded" mode (max_corr_dist larger than the grid can bin, e.g. PCL's default sqrt(DBL_MAX)) uses the
 // brute-force exact NN of grid.cu instead of the grid.
 #include "grid.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include <float.h>
 #include <math.h>
+#include <limits.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -149,28 +153,36 @@ __device__ bool polar_rotation(const double* A, double* R) {
   const double det0 = det3(A);
   const double scale = sqrt(fro2 / 3.0);
   if (!(det0 > 1e-7 * scale * scale * scale)) return false;
-  for (int it = 0; it < 32; ++it) {
+  // Any positive scaling sequence converges to the same polar factor, so the scale g only needs float accuracy
+  // (rsqrtf) and is dropped once the iterate is nearly orthogonal; the loop then has no fp64 sqrt and one reciprocal.
+  bool scaling = true;
+  for (int it = 0; it < 40; ++it) {
     const double c[9] = {X[4] * X[8] - X[5] * X[7], X[5] * X[6] - X[3] * X[8], X[3] * X[7] - X[4] * X[6],
                          X[2] * X[7] - X[1] * X[8], X[0] * X[8] - X[2] * X[6], X[1] * X[6] - X[0] * X[7],
                          X[1] * X[5] - X[2] * X[4], X[2] * X[3] - X[0] * X[5], X[0] * X[4] - X[1] * X[3]};
     const double det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
     if (!(det > 0.0)) return false;
-    const double idet = 1.0 / det;
-    double nx = 0, ny = 0;
-    for (int i = 0; i < 9; ++i) {
-      nx += X[i] * X[i];
-      ny += c[i] * c[i];
+    const double idet = __drcp_rn(det);
+    double a = 0.5, bq = 0.5 * idet;  // X <- a X + bq cof(X)   (cof(X) / det = X^-T)
+    if (scaling) {
+      double nx = 0, ny = 0;
+      for (int i = 0; i < 9; ++i) {
+        nx += X[i] * X[i];
+        ny += c[i] * c[i];
+      }
+      const float ratio = (float)(ny * idet * idet / nx);  // ||X^-T||_F^2 / ||X||_F^2
+      const float g = sqrtf(sqrtf(ratio));
+      if (fabsf(g - 1.0f) < 1e-2f) scaling = false;
+      a = 0.5 * (double)g;
+      bq = 0.5 * idet / (double)g;
     }
-    ny *= idet * idet;  // ||X^-T||_F^2 (c is the cofactor matrix = det * X^-T)
-    const double g = sqrt(sqrt(ny / nx));
-    double diff = 0, nn = 0;
+    double diff = 0;
     for (int i = 0; i < 9; ++i) {
-      const double v = 0.5 * (g * X[i] + c[i] * idet / g);
+      const double v = a * X[i] + bq * c[i];
       diff += (v - X[i]) * (v - X[i]);
-      nn += v * v;
       X[i] = v;
     }
-    if (diff <= 1e-30 * nn) break;
+    if (!scaling && diff <= 1e-22) break;  // quadratic convergence: the NEXT update would be ~1e-22, below fp64 resolution
   }
   for (int i = 0; i < 9; ++i) R[i] = X[i];
   return true;
@@ -409,6 +421,44 @@ __global__ void k_copy_work(const float4* __restrict__ src, const int* __restric
     work[(size_t)seg * stride_work + i] = src[(size_t)seg * stride_src + i];
 }
 
+// cell key of every source point (for the spatial sort of the working cloud: neighbouring lanes then query
+// neighbouring cells, which removes most of the divergence of the cell / candidate loops)
+__global__ void k_source_keys(const float4* __restrict__ src, const int* __restrict__ count, int stride, int pstride,
+                              float inv_cs, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  const int seg = blockIdx.y;
+  const int n = count[seg];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pstride; i += gridDim.x * blockDim.x) {
+    // padding entries sort to the end of THEIR segment's block, so block s always holds segment s
+    unsigned long long k = ((unsigned long long)(unsigned)seg << 48) | 0xFFFFFFFFFFFFull;
+    if (i < n) {
+      const float4 p = src[(size_t)seg * stride + i];
+      int ix = 0, iy = 0, iz = 0;
+      if (finite3(p.x, p.y, p.z)) {
+        ix = max(-32767, min(32766, __float2int_rd(__fmul_rn(p.x, inv_cs))));
+        iy = max(-32767, min(32766, __float2int_rd(__fmul_rn(p.y, inv_cs))));
+        iz = max(-32767, min(32766, __float2int_rd(__fmul_rn(p.z, inv_cs))));
+      }
+      k = ((unsigned long long)(unsigned)seg << 48) | ((unsigned long long)(unsigned)(iz + 32768) << 32) |
+          ((unsigned long long)(unsigned)(iy + 32768) << 16) | (unsigned long long)(unsigned)(ix + 32768);
+    }
+    keys[(size_t)seg * pstride + i] = k;
+    vals[(size_t)seg * pstride + i] = i;
+  }
+}
+
+// work[seg][j] = src[seg][perm[j]] with the original index kept in .w (rgba is not needed by the iterations)
+__global__ void k_copy_work_perm(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
+                                 const int* __restrict__ perm, int pstride, float4* __restrict__ work, int stride_work) {
+  const int seg = blockIdx.y;
+  const int n = count[seg];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int i = perm[(size_t)seg * pstride + j];
+    float4 p = src[(size_t)seg * stride_src + i];
+    p.w = __int_as_float(i);
+    work[(size_t)seg * stride_work + j] = p;
+  }
+}
+
 __global__ void k_gather_final(const IcpState* __restrict__ st, float* __restrict__ T, int n_seg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_seg * 16) T[i] = st[i / 16].final_T[i % 16];
@@ -421,6 +471,8 @@ __global__ void k_pack_i32(const int* __restrict__ v, const int* __restrict__ co
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[off[seg] + i] = v[(size_t)seg * stride + i];
 }
+
+#include "icp_persist.cuh"
 
 }  // namespace
 
@@ -435,6 +487,9 @@ extern "C" void rspcl_icp_reference_params(rspcl_icp_params* p) {
 
 // Device-level align used by rspcl_icp_align and the pairwise pipeline.  d_guess: n_seg x 16 floats on the device or
 // null.  h_results: host array (prev_mse read as input).  Synchronises before returning.
+int radix_sort_pairs(rspcl_ctx* ctx, unsigned long long* keys, int* vals, unsigned long long* tmp_keys, int* tmp_vals,
+                     long long n);
+
 int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
                      const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, int* d_first_corr) {
   const int S = src->n_seg;
@@ -482,9 +537,101 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   k_copy_work<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, work, wstride);
   LAUNCH_CHECK(ctx);
 
+  // ---- persistent shared-memory path: one cluster per pair, all iterations in one launch (icp_persist.cuh)
+  bool persist_done = false;
+  {
+    const char* env = getenv("RSPCL_ICP_PERSIST");
+    const bool want = !(env && env[0] == '0');
+    if (want && !brute && tgt->max_count_hint <= P_NTMAX && src->max_count_hint > 0 && src->max_count_hint < 65536) {
+      int* d_status = nullptr;
+      CU(ctx, scratch_alloc(ctx, &d_status, (size_t)S));
+      CU(ctx, cudaMemsetAsync(d_status, 0, (size_t)S * sizeof(int), ctx->stream));
+      const int cl = (4 * S <= ctx->sm_count) ? 4 : ((2 * S <= ctx->sm_count) ? 2 : 1);
+      const float inv_cs_p = 1.0f / (float)(prm->max_corr_dist * 4.1);
+      {  // spatially sorted working cloud
+        const int pstride = src->max_count_hint;
+        const long long N = (long long)S * pstride;
+        unsigned long long *keys = nullptr, *tkeys = nullptr;
+        int *vals = nullptr, *tvals = nullptr;
+        CU(ctx, scratch_alloc(ctx, &keys, (size_t)N));
+        CU(ctx, scratch_alloc(ctx, &tkeys, (size_t)N));
+        CU(ctx, scratch_alloc(ctx, &vals, (size_t)N));
+        CU(ctx, scratch_alloc(ctx, &tvals, (size_t)N));
+        dim3 gk(blocks_per_seg(ctx, S, pstride, 256), S);
+        k_source_keys<<<gk, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, pstride, inv_cs_p, keys, vals);
+        LAUNCH_CHECK(ctx);
+        int rcs = radix_sort_pairs(ctx, keys, vals, tkeys, tvals, N);
+        if (rcs) return rcs;
+        k_copy_work_perm<<<gk, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, vals, pstride, work, wstride);
+        LAUNCH_CHECK(ctx);
+        scratch_free(ctx, keys);
+        scratch_free(ctx, tkeys);
+        scratch_free(ctx, vals);
+        scratch_free(ctx, tvals);
+      }
+      static bool attr_set = false;
+      if (!attr_set) {
+        CU(ctx, cudaFuncSetAttribute(k_icp_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
+        CU(ctx, cudaFuncSetAttribute(k_icp_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
+        CU(ctx, cudaFuncSetAttribute(k_icp_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
+        attr_set = true;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(cl * S));
+      cfg.blockDim = dim3(P_THREADS);
+      cfg.dynamicSmemBytes = sizeof(PersistSmem);
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)cl;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      const int* cnt_p = src->count;
+      const float4* tp = tgt->pts;
+      const int* tc = tgt->count;
+      int tstride_p = tgt->stride, ws = wstride, sh = shared_target;
+      ProfScope prof(ctx, "k_icp_persist", 0.0);
+      cudaError_t le;
+      if (cl == 4)
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status);
+      else if (cl == 2)
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status);
+      else
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status);
+      CU(ctx, le);
+      LAUNCH_CHECK(ctx);
+      prof.end();
+      std::vector<int> hs(S);
+      std::vector<IcpState> hst0(S);
+      std::vector<int> hc(S);
+      CU(ctx, cudaMemcpyAsync(hs.data(), d_status, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(ctx, cudaMemcpyAsync(hst0.data(), st, (size_t)S * sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(ctx, cudaMemcpyAsync(hc.data(), src->count, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(ctx, cudaStreamSynchronize(ctx->stream));
+      scratch_free(ctx, d_status);
+      bool fallback = false;
+      double units = 0;
+      for (int s = 0; s < S; ++s) {
+        if (hs[s]) fallback = true;
+        units += (double)hc[s] * (hst0[s].iterations > 0 ? hst0[s].iterations : 1);
+      }
+      prof.set_units(units);
+      if (!fallback) {
+        persist_done = true;
+      } else {  // a target did not fit the shared-memory grid: redo the whole batch on the global-memory path
+        k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, S);
+        LAUNCH_CHECK(ctx);
+        k_copy_work<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, work, wstride);
+        LAUNCH_CHECK(ctx);
+      }
+    }
+  }
+
   DevGrid g;
   g.shared_target = shared_target;
-  if (!brute) {
+  if (!brute && !persist_done) {
     ProfScope prof(ctx, "grid_build", (double)S * tgt->max_count_hint);
     int rc = grid_build(ctx, tgt, cs, &g, d_range);
     if (rc) return rc;
@@ -493,9 +640,9 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   // iteration loop: launches are enqueued in growing chunks; the host only looks at the active-pair counter
   // between chunks (1, 1, 2, 4, 8, ... iterations), so the reference's one-iteration aligns cost one read-back.
   dim3 gstep(nblk, S);
-  int done_iters = 0, chunk = 1, active = S;
+  int done_iters = 0, chunk = 1, active = persist_done ? 0 : S;
   double prof_units = 0;  // source points per launch (all pairs; converged pairs exit early)
-  if (ctx->prof_on) {
+  if (ctx->prof_on && !persist_done) {
     std::vector<int> c(S);
     CU(ctx, cudaMemcpyAsync(c.data(), src->count, S * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -545,7 +692,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     h_results[s].mse = hst[s].mse;
     h_results[s].prev_mse = hst[s].prev_mse;
   }
-  if (!brute) grid_free(ctx, &g);
+  if (!brute && !persist_done) grid_free(ctx, &g);
   scratch_free(ctx, work);
   scratch_free(ctx, st);
   scratch_free(ctx, partials);

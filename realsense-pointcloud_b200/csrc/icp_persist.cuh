@@ -1,0 +1,322 @@
+// icp_persist.cuh -- persistent, shared-memory-resident ICP: one thread-block cluster per (source, target) pair runs
+// EVERY iteration of align() inside a single launch.  (Included by icp.cu inside its anonymous namespace.)
+//
+// Why: edge clouds are ~10^4 points, so a per-iteration launch is bound by dependent L2 round trips and launch
+// latency, not by HBM (profiles/r01_v1_summary.md).  B200 gives 227 KB of shared memory per CTA: the whole
+// voxel-filtered target (<= 12288 points as SoA x/y/z + 16-bit original index = 168 KB) and its cell table (4096 x 8 B)
+// fit in one SM, so every neighbour-cell probe and candidate read becomes an LDS (~30 cycles) instead of an L2 access
+// (~300+ cycles), the convergence test never leaves the SM and the host never polls.
+//   * cluster of CL CTAs per pair (CL = 4, 2 or 1 chosen from the batch size so the chip is filled): every CTA holds
+//     a full replica of the target grid and owns 1/CL of the source points; the 17 fp64 partial sums are exchanged
+//     through distributed shared memory (cluster.map_shared_rank) and each CTA redundantly runs the same solve, so no
+//     broadcast is needed and all CTAs of a pair take the same convergence decision.
+//   * the working source cloud stays in global memory (L2-resident, coalesced 16 B loads/stores, one independent
+//     round trip per point per iteration) and is updated in place exactly like PCL's input_transformed.
+// Exactness is unchanged: cells are 4.1 x the gate, the gate ball touches <= 2x2x2 cells, distances use the FLANN
+// L2_Simple order, ties go to the lowest original index.
+#pragma once
+// (icp.cu includes <cooperative_groups.h> and defines `cg` before entering its anonymous namespace)
+
+constexpr int P_THREADS = 512;
+constexpr int P_NTMAX = 12288;                 // target points resident per CTA
+constexpr int P_CAP = 4096;                    // cell-table slots (power of two)
+constexpr unsigned P_EMPTY = 0xFFFFFFFFu;
+constexpr int P_WARPS = P_THREADS / 32;
+
+struct PersistSmem {
+  float tx[P_NTMAX], ty[P_NTMAX], tz[P_NTMAX];
+  unsigned short tidx[P_NTMAX];
+  uint2 tab[P_CAP];                 // {key, start << 16 | count}
+  unsigned short fill[P_CAP];       // build-time cursors
+  double red[P_WARPS][NRED];
+  double part[2][NRED];             // this CTA's partial sums, double-buffered by iteration parity (read by the
+                                    // other CTAs of the cluster through DSMEM)
+  double tot[NRED];
+  IcpState st;                      // replicated per CTA
+  float M[16];
+  int origin[3];                    // minimum cell coordinates of the target
+  int cmax[3];
+  int flags[4];                     // [0] build failed -> fallback, [1] dummy active counter
+};
+
+__device__ __forceinline__ unsigned p_hash(unsigned key) { return (key * 0x9E3779B1u) >> (32 - 12); }  // log2(P_CAP) = 12
+static_assert(P_CAP == 4096, "p_hash assumes 4096 slots");
+
+__device__ __forceinline__ int p_cell(float v, float inv_cs) { return __float2int_rd(__fmul_rn(v, inv_cs)); }
+
+template <int CL>
+__global__ void __launch_bounds__(P_THREADS, 1)
+k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstride, IcpState* __restrict__ st_g,
+              const float4* __restrict__ tgt, const int* __restrict__ tcount, int tstride, int shared_target,
+              IcpDevParams prm, float inv_cs, int* __restrict__ first_corr, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char p_smem_raw[];
+  PersistSmem& S = *reinterpret_cast<PersistSmem*>(p_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int pair = blockIdx.x / CL;
+  const int crank = (CL > 1) ? (int)cg::this_cluster().block_rank() : 0;
+  const int tseg = shared_target ? 0 : pair;
+  const int nt = tcount[tseg];
+  const int ns = count[pair];
+  const float4* T = tgt + (size_t)tseg * tstride;
+
+  // ---------------------------------------------------------------- build the target replica in shared memory
+  if (tid == 0) {
+    S.origin[0] = S.origin[1] = S.origin[2] = INT_MAX;
+    S.cmax[0] = S.cmax[1] = S.cmax[2] = INT_MIN;
+    S.flags[0] = (nt > P_NTMAX) ? 1 : 0;
+    S.flags[1] = 1;
+    S.st = st_g[pair];
+  }
+  for (int k = tid; k < P_CAP; k += P_THREADS) {
+    S.tab[k] = make_uint2(P_EMPTY, 0u);
+    S.fill[k] = 0;
+  }
+  __syncthreads();
+  const bool too_big = S.flags[0] != 0;
+  if (!too_big) {
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (int i = tid; i < nt; i += P_THREADS) {
+      const float4 p = T[i];
+      if (!finite3(p.x, p.y, p.z)) continue;
+      const int c[3] = {p_cell(p.x, inv_cs), p_cell(p.y, inv_cs), p_cell(p.z, inv_cs)};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = min(mn[a], c[a]);
+        mx[a] = max(mx[a], c[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+        mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+      }
+      if (lane == 0) {
+        atomicMin(&S.origin[a], mn[a]);
+        atomicMax(&S.cmax[a], mx[a]);
+      }
+    }
+  }
+  __syncthreads();
+  if (!too_big && tid == 0) {
+    for (int a = 0; a < 3; ++a)
+      if (S.cmax[a] >= S.origin[a] && (long long)S.cmax[a] - S.origin[a] > 1022) S.flags[0] = 1;  // 10-bit local coordinates
+  }
+  __syncthreads();
+  const int ox = S.origin[0], oy = S.origin[1], oz = S.origin[2];
+  // pass A: insert cells, count points per cell
+  if (!S.flags[0]) {
+    for (int i = tid; i < nt; i += P_THREADS) {
+      const float4 p = T[i];
+      if (!finite3(p.x, p.y, p.z)) continue;
+      const unsigned key = ((unsigned)(p_cell(p.x, inv_cs) - ox) << 20) | ((unsigned)(p_cell(p.y, inv_cs) - oy) << 10) |
+                           (unsigned)(p_cell(p.z, inv_cs) - oz);
+      unsigned s = p_hash(key);
+      int probes = 0;
+      while (true) {
+        const unsigned prev = atomicCAS(&S.tab[s].x, P_EMPTY, key);
+        if (prev == P_EMPTY || prev == key) break;
+        s = (s + 1) & (P_CAP - 1);
+        if (++probes >= P_CAP) {  // table full: this pair goes to the global-memory path
+          S.flags[0] = 1;
+          break;
+        }
+      }
+      if (probes < P_CAP) atomicAdd(&S.tab[s].y, 1u);
+    }
+  }
+  __syncthreads();
+  {  // keep the load factor <= 0.85 so that probes of absent cells always terminate quickly
+    int occ = 0;
+    for (int k = tid; k < P_CAP; k += P_THREADS) occ += (S.tab[k].x != P_EMPTY) ? 1 : 0;
+    const int total = __syncthreads_count(0) + 0;  // barrier
+    (void)total;
+    int* wtot = reinterpret_cast<int*>(&S.red[0][0]);
+    for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
+    if (lane == 0) wtot[wid] = occ;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < P_WARPS; ++w) t += wtot[w];
+      if (t > (P_CAP * 85) / 100) S.flags[0] = 1;
+    }
+    __syncthreads();
+  }
+  if (S.flags[0]) {  // uniform across the CTA (and across the cluster: every CTA builds the same replica)
+    if (tid == 0 && crank == 0) status[pair] = 1;
+    return;
+  }
+  // exclusive scan of the per-slot counts -> start offsets (P_CAP / P_THREADS slots per thread)
+  {
+    constexpr int PER = P_CAP / P_THREADS;
+    int loc[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      loc[k] = (int)S.tab[tid * PER + k].y;
+      sum += loc[k];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int* wtot = reinterpret_cast<int*>(&S.red[0][0]);
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int v = lane < P_WARPS ? wtot[lane] : 0, vi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, vi, o);
+        if (lane >= o) vi += t;
+      }
+      if (lane < P_WARPS) wtot[lane] = vi - v;
+    }
+    __syncthreads();
+    int excl = wtot[wid] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      S.tab[tid * PER + k].y = ((unsigned)excl << 16) | (unsigned)loc[k];
+      excl += loc[k];
+    }
+  }
+  __syncthreads();
+  // pass B: scatter the points into cell order
+  for (int i = tid; i < nt; i += P_THREADS) {
+    const float4 p = T[i];
+    if (!finite3(p.x, p.y, p.z)) continue;
+    const unsigned key = ((unsigned)(p_cell(p.x, inv_cs) - ox) << 20) | ((unsigned)(p_cell(p.y, inv_cs) - oy) << 10) |
+                         (unsigned)(p_cell(p.z, inv_cs) - oz);
+    unsigned s = p_hash(key);
+    while (S.tab[s].x != key) s = (s + 1) & (P_CAP - 1);
+    // 16-bit cursors: atomicAdd on the containing 32-bit word
+    unsigned* wordp = reinterpret_cast<unsigned*>(S.fill) + (s >> 1);
+    const unsigned sh = (s & 1u) * 16u;
+    const unsigned old = atomicAdd(wordp, 1u << sh);
+    const int pos = (int)(S.tab[s].y >> 16) + (int)((old >> sh) & 0xFFFFu);
+    S.tx[pos] = p.x;
+    S.ty[pos] = p.y;
+    S.tz[pos] = p.z;
+    S.tidx[pos] = (unsigned short)i;
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- iterations
+  float4* W = work + (size_t)pair * wstride;
+  const float r = prm.search_r;
+  const int span = S.cmax[0] - ox, spany = S.cmax[1] - oy, spanz = S.cmax[2] - oz;
+  int parity = 0;
+  while (true) {
+    if (tid < 16) S.M[tid] = S.st.inc_T[tid];
+    __syncthreads();
+    const int apply = S.st.apply_inc;
+    const bool want_corr = first_corr != nullptr && S.st.iterations == 0;
+    double acc[NRED];
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+    for (int i = crank * P_THREADS + tid; i < ns; i += CL * P_THREADS) {
+      float4 p = W[i];
+      const bool fin = finite3(p.x, p.y, p.z);
+      if (apply && fin) {
+        const float3 q = xform_point(S.M, p.x, p.y, p.z);
+        p.x = q.x;
+        p.y = q.y;
+        p.z = q.z;
+      }
+      // .w = (previous match slot + 1) << 16 | original source index
+      const unsigned wbits = __float_as_uint(p.w);
+      const int orig = (int)(wbits & 0xFFFFu);
+      const int kp = (int)(wbits >> 16) - 1;
+      int best = -1, kbest = 0;
+      float bd = INFINITY;
+      if (fin) {
+        // Temporal coherence, still exact: the previous iteration's match bounds the NN distance from above, so only
+        // cells touched by the ball of THAT radius can hold a closer (or equal, lower-index) point.
+        float rr = r;
+        if (kp >= 0) {
+          bd = dist2_l2simple(p.x, p.y, p.z, S.tx[kp], S.ty[kp], S.tz[kp]);
+          best = (int)S.tidx[kp];
+          kbest = kp;
+          rr = fminf(r, __fmaf_rn(sqrtf(bd), 1.0001f, 1e-7f));
+        }
+        const int x0 = p_cell(p.x - rr, inv_cs) - ox, x1 = p_cell(p.x + rr, inv_cs) - ox;
+        const int y0 = p_cell(p.y - rr, inv_cs) - oy, y1 = p_cell(p.y + rr, inv_cs) - oy;
+        const int z0 = p_cell(p.z - rr, inv_cs) - oz, z1 = p_cell(p.z + rr, inv_cs) - oz;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0)) continue;
+          const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
+          if ((unsigned)ix > (unsigned)span || (unsigned)iy > (unsigned)spany || (unsigned)iz > (unsigned)spanz) continue;
+          const unsigned key = ((unsigned)ix << 20) | ((unsigned)iy << 10) | (unsigned)iz;
+          unsigned s = p_hash(key);
+          uint2 e = S.tab[s];
+          while (e.x != key && e.x != P_EMPTY) {
+            s = (s + 1) & (P_CAP - 1);
+            e = S.tab[s];
+          }
+          if (e.x != key) continue;
+          const int b = (int)(e.y >> 16), en = b + (int)(e.y & 0xFFFFu);
+          for (int k = b; k < en; ++k) {
+            const float d = dist2_l2simple(p.x, p.y, p.z, S.tx[k], S.ty[k], S.tz[k]);
+            const int idx = (int)S.tidx[k];
+            if (d < bd || (d == bd && idx < best)) {
+              bd = d;
+              best = idx;
+              kbest = k;
+            }
+          }
+        }
+      }
+      p.w = __uint_as_float(((unsigned)(best >= 0 ? kbest + 1 : 0) << 16) | (unsigned)orig);
+      W[i] = p;
+      const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
+      if (want_corr) first_corr[(size_t)pair * wstride + orig] = ok ? best : -1;
+      if (ok) {
+        const double sx = p.x, sy = p.y, sz = p.z, tx = S.tx[kbest], ty = S.ty[kbest], tz = S.tz[kbest];
+        acc[0] += 1.0;
+        acc[1] += sx; acc[2] += sy; acc[3] += sz;
+        acc[4] += tx; acc[5] += ty; acc[6] += tz;
+        acc[7] += sx * tx; acc[8] += sx * ty; acc[9] += sx * tz;
+        acc[10] += sy * tx; acc[11] += sy * ty; acc[12] += sy * tz;
+        acc[13] += sz * tx; acc[14] += sz * ty; acc[15] += sz * tz;
+        acc[16] += (double)bd;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) {
+      const double v = warp_sum(acc[k]);
+      if (lane == 0) S.red[wid][k] = v;
+    }
+    __syncthreads();
+    const int buf = parity;
+    parity ^= 1;
+    if (tid < NRED) {
+      double v = 0;
+#pragma unroll
+      for (int w = 0; w < P_WARPS; ++w) v += S.red[w][tid];
+      S.part[buf][tid] = v;
+    }
+    if (CL > 1) {
+      // One cluster barrier per iteration: buffer `buf` is rewritten two iterations later, after every CTA has passed
+      // the next barrier, i.e. after every CTA has finished reading it.
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();
+      if (tid < NRED) {
+        double v = 0;
+        for (int rk = 0; rk < CL; ++rk) v += *cluster.map_shared_rank(&S.part[buf][tid], rk);  // fixed rank order
+        S.tot[tid] = v;
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      if (tid < NRED) S.tot[tid] = S.part[buf][tid];
+      __syncthreads();
+    }
+    if (tid == 0) icp_solve_pair(&S.st, S.tot, prm, &S.flags[1]);
+    __syncthreads();
+    if (S.st.done) break;
+  }
+  if (CL > 1) cg::this_cluster().sync();  // no CTA leaves while a sibling may still read its partials
+  if (tid == 0 && crank == 0) st_g[pair] = S.st;
+}
