@@ -44,6 +44,10 @@ int rspcl_ctx_sync(rspcl_ctx* ctx);
 /* CUDA-event timer on the context's stream (the stream every kernel of this library is launched on). */
 int rspcl_timer_start(rspcl_ctx* ctx);
 int rspcl_timer_stop(rspcl_ctx* ctx, float* elapsed_ms);   /* synchronises */
+/* Device time spanned by several contexts working concurrently (one stream each): the largest elapsed time between
+ * any context's rspcl_timer_start event and any context's rspcl_timer_mark event.  Synchronises all of them. */
+int rspcl_timer_mark(rspcl_ctx* ctx);
+int rspcl_timer_span(rspcl_ctx* const* ctxs, int n, float* elapsed_ms);
 /* number of kernels this library has launched on the context since creation */
 long long rspcl_launch_count(const rspcl_ctx* ctx);
 /* Per-kernel CUDA-event profile (off by default).  While enabled, the library brackets the launches of its main

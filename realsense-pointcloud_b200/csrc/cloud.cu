@@ -4,8 +4,72 @@
 // (pcl::transformPointCloud), icp:57,119-120 / ndt:55,107-108 / incr:64 (operator+), blur_filter.hpp:18-36.
 // All kernels are streaming, HBM-bound: 128-bit loads/stores, grids sized in multiples of the SM count.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------ context
+__global__ void k_copy_words(unsigned* __restrict__ dst, const unsigned* __restrict__ src, int n_words) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+__global__ void k_copy_bytes(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+static char* z_take(rspcl_ctx* ctx, size_t bytes) {
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (!ctx->z_host || ctx->z_used + need > ctx->z_cap) return nullptr;
+  char* p = ctx->z_host + ctx->z_used;
+  ctx->z_used += need;
+  return p;
+}
+
+cudaError_t small_h2d(rspcl_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  char* slot = (bytes <= (64u << 10) && bytes % 4 == 0) ? z_take(ctx, bytes) : nullptr;
+  if (!slot) return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);  // large: plain staged copy
+  memcpy(slot, h_src, bytes);
+  const int nw = (int)(bytes / 4);
+  k_copy_words<<<(nw + 255) / 256 > 8 ? 8 : (nw + 255) / 256, 256, 0, ctx->stream>>>((unsigned*)d_dst, (const unsigned*)slot, nw);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t small_d2h(rspcl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  char* slot = (bytes <= (64u << 10) && bytes % 4 == 0 && ((size_t)d_src & 3) == 0) ? z_take(ctx, bytes) : nullptr;
+  if (!slot) {
+    // large or odd-sized read-back (masks, index dumps): a pinned, mapped bounce buffer filled by a copy kernel and
+    // copied out at ctx_sync() -- never an asynchronous copy straight into pageable user memory.
+    void* bounce = nullptr;
+    cudaError_t e = cudaHostAlloc(&bounce, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) return e;
+    if (bytes % 4 == 0 && ((size_t)d_src & 3) == 0)
+      k_copy_words<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>((unsigned*)bounce, (const unsigned*)d_src, (int)(bytes / 4));
+    else
+      k_copy_bytes<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>((unsigned char*)bounce, (const unsigned char*)d_src, bytes);
+    ctx->launches++;
+    ctx->z_pending.push_back({h_dst, bounce, bytes, bounce});
+    return cudaGetLastError();
+  }
+  const int nw = (int)(bytes / 4);
+  k_copy_words<<<(nw + 255) / 256 > 8 ? 8 : (nw + 255) / 256, 256, 0, ctx->stream>>>((unsigned*)slot, (const unsigned*)d_src, nw);
+  ctx->launches++;
+  ctx->z_pending.push_back({h_dst, slot, bytes, nullptr});
+  return cudaGetLastError();
+}
+
+cudaError_t ctx_sync(rspcl_ctx* ctx) {
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return e;
+  for (auto& p : ctx->z_pending) {
+    memcpy(p.dst, p.src, p.n);
+    if (p.owned) cudaFreeHost(p.owned);
+  }
+  ctx->z_pending.clear();
+  ctx->z_used = 0;  // everything enqueued so far has executed: the arena can be recycled
+  return cudaSuccess;
+}
+
 int ensure_stage(rspcl_ctx* ctx, size_t bytes) {
   if (ctx->h_stage_bytes >= bytes) return RSPCL_OK;
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -30,11 +94,27 @@ extern "C" int rspcl_ctx_create(int device, rspcl_ctx** out) {
     return RSPCL_ERR_CUDA;
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-  // keep freed scratch in the stream-ordered pool: after warm-up no call touches the driver allocator
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+  if (cudaHostAlloc((void**)&c->z_host, 4u << 20, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+    c->z_cap = 4u << 20;
+  } else {
+    c->z_host = nullptr;
+    cudaGetLastError();
+  }
+  // Private stream-ordered pool that keeps freed scratch: after warm-up no call touches the driver allocator, and
+  // because the pool belongs to this context's single stream the allocator never inserts a dependency on another
+  // context's work (contexts used from different host threads overlap freely).
+  cudaMemPoolProps props;
+  memset(&props, 0, sizeof(props));
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  if (cudaMemPoolCreate(&c->pool, &props) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  } else {
+    c->pool = nullptr;
+    cudaGetLastError();
   }
   *out = c;
   return RSPCL_OK;
@@ -43,8 +123,10 @@ extern "C" int rspcl_ctx_create(int device, rspcl_ctx** out) {
 extern "C" void rspcl_ctx_destroy(rspcl_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  ctx_sync(ctx);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+  if (ctx->z_host) cudaFreeHost(ctx->z_host);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -54,7 +136,7 @@ extern "C" void rspcl_ctx_destroy(rspcl_ctx* ctx) {
 extern "C" const char* rspcl_last_error(const rspcl_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 extern "C" int rspcl_ctx_sync(rspcl_ctx* ctx) {
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   return RSPCL_OK;
 }
 extern "C" int rspcl_timer_start(rspcl_ctx* ctx) {
@@ -67,10 +149,27 @@ extern "C" int rspcl_timer_stop(rspcl_ctx* ctx, float* ms) {
   CU(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
   return RSPCL_OK;
 }
+extern "C" int rspcl_timer_mark(rspcl_ctx* ctx) {
+  CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  return RSPCL_OK;
+}
+extern "C" int rspcl_timer_span(rspcl_ctx* const* ctxs, int n, float* ms) {
+  if (!ctxs || n <= 0 || !ms) return RSPCL_ERR_ARG;
+  float best = 0.f;
+  for (int j = 0; j < n; ++j) CU(ctxs[j], cudaEventSynchronize(ctxs[j]->ev1));
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      float t = 0.f;
+      CU(ctxs[i], cudaEventElapsedTime(&t, ctxs[i]->ev0, ctxs[j]->ev1));
+      if (t > best) best = t;
+    }
+  *ms = best;
+  return RSPCL_OK;
+}
 extern "C" long long rspcl_launch_count(const rspcl_ctx* ctx) { return ctx->launches; }
 
 static int prof_drain(rspcl_ctx* ctx) {
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   for (auto& r : ctx->prof_recs) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
@@ -141,7 +240,7 @@ extern "C" int rspcl_cloud_create(rspcl_ctx* ctx, int n_seg, int stride, rspcl_c
 
 extern "C" void rspcl_cloud_destroy(rspcl_ctx* ctx, rspcl_cloud* c) {
   if (!c) return;
-  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (ctx) ctx_sync(ctx);
   cudaFree(c->pts);
   cudaFree(c->count);
   if (c->gray) cudaFree(c->gray);
@@ -205,6 +304,19 @@ __global__ void k_pack(const float4* __restrict__ pts, const int* __restrict__ o
   }
 }
 
+// Bulk host<->device copies are issued in pieces so that the small control copies of OTHER contexts (counts, results)
+// interleave on the copy engine instead of queueing behind one multi-millisecond DMA (contexts are pipelined from
+// several host threads; copy engines serve whole operations in submission order).
+static cudaError_t chunked_copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
+  const size_t piece = 4u << 20;
+  for (size_t off = 0; off < bytes; off += piece) {
+    const size_t n = bytes - off < piece ? bytes - off : piece;
+    cudaError_t e = cudaMemcpyAsync((char*)dst + off, (const char*)src + off, n, kind, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 int blocks_per_seg(const rspcl_ctx* ctx, int n_seg, int max_count, int threads) {
   // grid-stride kernels: cover max_count once if the chip has room, else cap the batch at ~16 CTAs per SM
   int want = div_up(max_count, threads);
@@ -243,10 +355,10 @@ extern "C" int rspcl_cloud_upload(rspcl_ctx* ctx, rspcl_cloud* c, const void* ho
   CU(ctx, scratch_alloc(ctx, &d_off, (size_t)n_seg + 1));
   CU(ctx, scratch_alloc(ctx, (char**)&raw, (size_t)total * esz));
   // small pageable copies: the runtime stages them before returning, so the host vectors may go out of scope
-  CU(ctx, cudaMemcpyAsync(d_off, off.data(), (n_seg + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(c->count, counts, n_seg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, small_h2d(ctx, d_off, off.data(), (n_seg + 1) * sizeof(int)));
+  CU(ctx, small_h2d(ctx, c->count, counts, n_seg * sizeof(int)));
   if (total > 0) {
-    CU(ctx, cudaMemcpyAsync(raw, host, (size_t)total * esz, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, chunked_copy(raw, host, (size_t)total * esz, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid(blocks_per_seg(ctx, n_seg, maxc, 256), n_seg);
     ProfScope prof(ctx, "k_unpack", (double)total);
     if (layout == RSPCL_LAYOUT_PCL32)
@@ -263,8 +375,8 @@ extern "C" int rspcl_cloud_upload(rspcl_ctx* ctx, rspcl_cloud* c, const void* ho
 extern "C" int rspcl_cloud_counts(rspcl_ctx* ctx, const rspcl_cloud* c, int32_t* counts) {
   if (!ctx || !c || !counts) return RSPCL_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, cudaMemcpyAsync(counts, c->count, c->n_seg * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, small_d2h(ctx, counts, c->count, c->n_seg * sizeof(int)));
+  CU(ctx, ctx_sync(ctx));
   return RSPCL_OK;
 }
 
@@ -293,15 +405,15 @@ extern "C" int rspcl_cloud_download(rspcl_ctx* ctx, const rspcl_cloud* c, void* 
   void* raw = nullptr;
   CU(ctx, scratch_alloc(ctx, &d_off, (size_t)c->n_seg + 1));
   CU(ctx, scratch_alloc(ctx, (char**)&raw, (size_t)total * esz));
-  CU(ctx, cudaMemcpyAsync(d_off, off.data(), (c->n_seg + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, small_h2d(ctx, d_off, off.data(), (c->n_seg + 1) * sizeof(int)));
   dim3 grid(blocks_per_seg(ctx, c->n_seg, maxc, 256), c->n_seg);
   if (layout == RSPCL_LAYOUT_PCL32)
     k_pack<true><<<grid, 256, 0, ctx->stream>>>(c->pts, d_off, c->count, raw, c->stride);
   else
     k_pack<false><<<grid, 256, 0, ctx->stream>>>(c->pts, d_off, c->count, raw, c->stride);
   LAUNCH_CHECK(ctx);
-  CU(ctx, cudaMemcpyAsync(host, raw, (size_t)total * esz, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, chunked_copy(host, raw, (size_t)total * esz, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   scratch_free(ctx, d_off);
   scratch_free(ctx, (char*)raw);
   return RSPCL_OK;
@@ -352,7 +464,7 @@ extern "C" int rspcl_transform(rspcl_ctx* ctx, const rspcl_cloud* in, const floa
   const int nT = broadcast ? 1 : in->n_seg;
   float* d_T = nullptr;
   CU(ctx, scratch_alloc(ctx, &d_T, (size_t)nT * 16));
-  CU(ctx, cudaMemcpyAsync(d_T, T, (size_t)nT * 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, small_h2d(ctx, d_T, T, (size_t)nT * 16 * sizeof(float)));
   int rc = transform_device(ctx, in, d_T, broadcast, out);
   scratch_free(ctx, d_T);
   return rc;
@@ -389,8 +501,8 @@ extern "C" int rspcl_concat(rspcl_ctx* ctx, const rspcl_cloud* a, const rspcl_cl
                                           out->stride, d_over);
   LAUNCH_CHECK(ctx);
   int over = 0;
-  CU(ctx, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, small_d2h(ctx, &over, d_over, sizeof(int)));
+  CU(ctx, ctx_sync(ctx));
   scratch_free(ctx, d_over);
   if (over) RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "concat: output stride %d too small", out->stride);
   out->max_count_hint = hint < out->stride ? hint : out->stride;

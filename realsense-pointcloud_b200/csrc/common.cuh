@@ -13,12 +13,20 @@ struct rspcl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaMemPool_t pool = nullptr;  // private stream-ordered pool: scratch is never recycled across contexts/streams
   long long launches = 0;
   std::string err;
   int sm_count = 148;
   // grow-only pinned staging buffer for small result read-backs
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
+  // Zero-copy control channel: small host<->device transfers (counts, indices, 4x4 matrices, convergence states) go
+  // through a mapped pinned arena read/written by tiny kernels, so they never queue behind another context's bulk DMA
+  // on the copy engines.  Device->host items are copied out of the arena at the next ctx_sync().
+  char* z_host = nullptr;
+  size_t z_cap = 0, z_used = 0;
+  struct ZPending { void* dst; const void* src; size_t n; void* owned; };  // owned: pinned bounce buffer to free
+  std::vector<ZPending> z_pending;
   // optional per-kernel event profile
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int kernel; double units; };
@@ -98,6 +106,7 @@ struct rspcl_cloud {
 // stream-ordered scratch (cudaMallocAsync pool: no synchronisation after warm-up)
 template <typename T>
 static inline cudaError_t scratch_alloc(rspcl_ctx* ctx, T** p, size_t n) {
+  if (ctx->pool) return cudaMallocFromPoolAsync((void**)p, (n ? n : 1) * sizeof(T), ctx->pool, ctx->stream);
   return cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), ctx->stream);
 }
 template <typename T>
@@ -108,6 +117,9 @@ static inline void scratch_free(rspcl_ctx* ctx, T* p) {
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int ensure_stage(rspcl_ctx* ctx, size_t bytes);
+cudaError_t small_h2d(rspcl_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+cudaError_t small_d2h(rspcl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);  // valid after ctx_sync()
+cudaError_t ctx_sync(rspcl_ctx* ctx);
 int blocks_per_seg(const rspcl_ctx* ctx, int n_seg, int max_count, int threads);
 int transform_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float* d_T, int broadcast, rspcl_cloud* out);
 int ensure_gray(rspcl_ctx* ctx, rspcl_cloud* c);

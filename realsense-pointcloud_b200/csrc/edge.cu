@@ -14,6 +14,7 @@
 //   K1c k_block_count / k_seg_scan / k_scatter  mask -> ascending row-major compaction (copyPointCloud(indices)).
 // Roofline: HBM-bound; algorithmic bytes per pixel = 1 R (gray) + 1 W (class) for K1.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -348,13 +349,13 @@ extern "C" int rspcl_edge_extract(rspcl_ctx* ctx, const rspcl_cloud* frames, flo
   int over = 0;
   if (host_mask) {
     for (int s = 0; s < S; ++s)
-      CU(ctx, cudaMemcpyAsync(host_mask + (size_t)s * n, mask + (size_t)s * stride, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+      CU(ctx, small_d2h(ctx, host_mask + (size_t)s * n, mask + (size_t)s * stride, n));
+    CU(ctx, small_d2h(ctx, &over, d_over, sizeof(int)));
+    CU(ctx, ctx_sync(ctx));
   } else if (out_edges->stride < n) {
     // capacity below the worst case: the overflow flag must be checked (synchronises)
-    CU(ctx, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, small_d2h(ctx, &over, d_over, sizeof(int)));
+    CU(ctx, ctx_sync(ctx));
   }
   scratch_free(ctx, cls);
   scratch_free(ctx, strong);

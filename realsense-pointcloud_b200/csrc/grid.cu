@@ -261,13 +261,13 @@ extern "C" int rspcl_nearest(rspcl_ctx* ctx, const rspcl_cloud* query, const rsp
     CU(ctx, scratch_alloc(ctx, &d_off, (size_t)query->n_seg));
     CU(ctx, scratch_alloc(ctx, &p_idx, (size_t)total));
     CU(ctx, scratch_alloc(ctx, &p_d2, (size_t)total));
-    CU(ctx, cudaMemcpyAsync(d_off, off.data(), query->n_seg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, small_h2d(ctx, d_off, off.data(), query->n_seg * sizeof(int)));
     dim3 grid(blocks_per_seg(ctx, query->n_seg, maxc, 256), query->n_seg);
     k_pack_nn<<<grid, 256, 0, ctx->stream>>>(d_idx, d_d2, query->count, d_off, query->stride, p_idx, p_d2);
     LAUNCH_CHECK(ctx);
-    CU(ctx, cudaMemcpyAsync(host_idx, p_idx, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(host_d2, p_d2, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, small_d2h(ctx, host_idx, p_idx, (size_t)total * sizeof(int)));
+    CU(ctx, small_d2h(ctx, host_d2, p_d2, (size_t)total * sizeof(float)));
+    CU(ctx, ctx_sync(ctx));
     scratch_free(ctx, d_off);
     scratch_free(ctx, p_idx);
     scratch_free(ctx, p_d2);
@@ -297,8 +297,8 @@ extern "C" int rspcl_fitness(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl
   LAUNCH_CHECK(ctx);
   k_fitness_final<<<div_up(S, 128), 128, 0, ctx->stream>>>(d_part, nblk, S, d_out);
   LAUNCH_CHECK(ctx);
-  CU(ctx, cudaMemcpyAsync(fitness, d_out, S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, small_d2h(ctx, fitness, d_out, S * sizeof(double)));
+  CU(ctx, ctx_sync(ctx));
   scratch_free(ctx, d_idx);
   scratch_free(ctx, d_d2);
   scratch_free(ctx, d_part);

@@ -146,6 +146,7 @@ __device__ void svd3(const double* A_in, double* U, double* s, double* V) {
 __device__ bool polar_rotation(const double* A, double* R) {
   double X[9];
   double fro2 = 0;
+#pragma unroll
   for (int i = 0; i < 9; ++i) {
     X[i] = A[i];
     fro2 += A[i] * A[i];
@@ -156,6 +157,7 @@ __device__ bool polar_rotation(const double* A, double* R) {
   // Any positive scaling sequence converges to the same polar factor, so the scale g only needs float accuracy
   // (rsqrtf) and is dropped once the iterate is nearly orthogonal; the loop then has no fp64 sqrt and one reciprocal.
   bool scaling = true;
+#pragma unroll 1
   for (int it = 0; it < 40; ++it) {
     const double c[9] = {X[4] * X[8] - X[5] * X[7], X[5] * X[6] - X[3] * X[8], X[3] * X[7] - X[4] * X[6],
                          X[2] * X[7] - X[1] * X[8], X[0] * X[8] - X[2] * X[6], X[1] * X[6] - X[0] * X[7],
@@ -166,6 +168,7 @@ __device__ bool polar_rotation(const double* A, double* R) {
     double a = 0.5, bq = 0.5 * idet;  // X <- a X + bq cof(X)   (cof(X) / det = X^-T)
     if (scaling) {
       double nx = 0, ny = 0;
+#pragma unroll
       for (int i = 0; i < 9; ++i) {
         nx += X[i] * X[i];
         ny += c[i] * c[i];
@@ -177,6 +180,7 @@ __device__ bool polar_rotation(const double* A, double* R) {
       bq = 0.5 * idet / (double)g;
     }
     double diff = 0;
+#pragma unroll
     for (int i = 0; i < 9; ++i) {
       const double v = a * X[i] + bq * c[i];
       diff += (v - X[i]) * (v - X[i]);
@@ -184,6 +188,7 @@ __device__ bool polar_rotation(const double* A, double* R) {
     }
     if (!scaling && diff <= 1e-22) break;  // quadratic convergence: the NEXT update would be ~1e-22, below fp64 resolution
   }
+#pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = X[i];
   return true;
 }
@@ -194,7 +199,9 @@ __device__ void umeyama_from_moments(const double* S, float* T) {
   const double ms[3] = {S[1] * inv_n, S[2] * inv_n, S[3] * inv_n};
   const double mt[3] = {S[4] * inv_n, S[5] * inv_n, S[6] * inv_n};
   double sigma[9];  // sigma(r,c) = mean((t_r - mt_r)(s_c - ms_c))
+#pragma unroll
   for (int r = 0; r < 3; ++r)
+#pragma unroll
     for (int c = 0; c < 3; ++c) sigma[r * 3 + c] = S[7 + c * 3 + r] * inv_n - mt[r] * ms[c];
   double R[9];
   if (!polar_rotation(sigma, R)) {
@@ -202,15 +209,20 @@ __device__ void umeyama_from_moments(const double* S, float* T) {
     svd3(sigma, U, sv, V);
     const double d = det3(U) * det3(V);
     const double Sd[3] = {1.0, 1.0, d < 0 ? -1.0 : 1.0};
+#pragma unroll
     for (int r = 0; r < 3; ++r)
+#pragma unroll
       for (int c = 0; c < 3; ++c) {
         double acc = 0;
+#pragma unroll
         for (int k = 0; k < 3; ++k) acc += U[r * 3 + k] * Sd[k] * V[c * 3 + k];
         R[r * 3 + c] = acc;
       }
   }
   mat4_identity(T);
+#pragma unroll
   for (int r = 0; r < 3; ++r) {
+#pragma unroll
     for (int c = 0; c < 3; ++c) T[c * 4 + r] = (float)R[r * 3 + c];
     T[12 + r] = (float)(mt[r] - (R[r * 3 + 0] * ms[0] + R[r * 3 + 1] * ms[1] + R[r * 3 + 2] * ms[2]));
   }
@@ -219,7 +231,9 @@ __device__ void umeyama_from_moments(const double* S, float* T) {
 // C = A * B (column-major float), entries ((a0 b0 + a1 b1) + a2 b2) + a3 b3 un-fused, as the oracle
 __device__ void mat4_mul(const float* A, const float* B, float* C) {
   float R[16];
+#pragma unroll
   for (int c = 0; c < 4; ++c)
+#pragma unroll
     for (int r = 0; r < 4; ++r) {
       float s = fmul(A[0 * 4 + r], B[c * 4 + 0]);
       s = fadd(s, fmul(A[1 * 4 + r], B[c * 4 + 1]));
@@ -227,6 +241,7 @@ __device__ void mat4_mul(const float* A, const float* B, float* C) {
       s = fadd(s, fmul(A[3 * 4 + r], B[c * 4 + 3]));
       R[c * 4 + r] = s;
     }
+#pragma unroll
   for (int i = 0; i < 16; ++i) C[i] = R[i];
 }
 
@@ -271,6 +286,7 @@ __device__ void icp_solve_pair(IcpState* S, const double* sums, const IcpDevPara
   }
   float T[16];
   umeyama_from_moments(sums, T);
+#pragma unroll
   for (int i = 0; i < 16; ++i) S->inc_T[i] = T[i];
   S->apply_inc = 1;
   mat4_mul(T, S->final_T, S->final_T);
@@ -528,8 +544,8 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   CU(ctx, scratch_alloc(ctx, &d_T, (size_t)S * 16));
   std::vector<double> prev(S);
   for (int s = 0; s < S; ++s) prev[s] = h_results[s].prev_mse;
-  CU(ctx, cudaMemcpyAsync(d_prev, prev.data(), S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(n_active, &S, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, small_h2d(ctx, d_prev, prev.data(), S * sizeof(double)));
+  CU(ctx, small_h2d(ctx, n_active, &S, sizeof(int)));
   CU(ctx, cudaMemsetAsync(d_range, 0, sizeof(int), ctx->stream));
   k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, S);
   LAUNCH_CHECK(ctx);
@@ -606,10 +622,10 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       std::vector<int> hs(S);
       std::vector<IcpState> hst0(S);
       std::vector<int> hc(S);
-      CU(ctx, cudaMemcpyAsync(hs.data(), d_status, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(ctx, cudaMemcpyAsync(hst0.data(), st, (size_t)S * sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(ctx, cudaMemcpyAsync(hc.data(), src->count, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(ctx, cudaStreamSynchronize(ctx->stream));
+      CU(ctx, small_d2h(ctx, hs.data(), d_status, (size_t)S * sizeof(int)));
+      CU(ctx, small_d2h(ctx, hst0.data(), st, (size_t)S * sizeof(IcpState)));
+      CU(ctx, small_d2h(ctx, hc.data(), src->count, (size_t)S * sizeof(int)));
+      CU(ctx, ctx_sync(ctx));
       scratch_free(ctx, d_status);
       bool fallback = false;
       double units = 0;
@@ -644,8 +660,8 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   double prof_units = 0;  // source points per launch (all pairs; converged pairs exit early)
   if (ctx->prof_on && !persist_done) {
     std::vector<int> c(S);
-    CU(ctx, cudaMemcpyAsync(c.data(), src->count, S * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, small_d2h(ctx, c.data(), src->count, S * sizeof(int)));
+    CU(ctx, ctx_sync(ctx));
     for (int v : c) prof_units += v;
   }
   while (done_iters < prm->max_iterations && active > 0) {
@@ -666,23 +682,23 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       LAUNCH_CHECK(ctx);
     }
     done_iters += todo;
-    CU(ctx, cudaMemcpyAsync(&active, n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, small_d2h(ctx, &active, n_active, sizeof(int)));
+    CU(ctx, ctx_sync(ctx));
     if (done_iters > 1) chunk *= 2;
   }
 
   // results + aligned output (Registration::align: output = final applied to the original source)
   std::vector<IcpState> hst(S);
   int range = 0;
-  CU(ctx, cudaMemcpyAsync(hst.data(), st, S * sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(&range, d_range, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, small_d2h(ctx, hst.data(), st, S * sizeof(IcpState)));
+  CU(ctx, small_d2h(ctx, &range, d_range, sizeof(int)));
   int rc = RSPCL_OK;
   if (aligned) {
     k_gather_final<<<div_up(S * 16, 256), 256, 0, ctx->stream>>>(st, d_T, S);
     LAUNCH_CHECK(ctx);
     rc = transform_device(ctx, src, d_T, 0, aligned);
   }
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   for (int s = 0; s < S; ++s) {
     memcpy(h_results[s].T, hst[s].final_T, sizeof(float) * 16);
     h_results[s].converged = hst[s].converged;
@@ -707,8 +723,8 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
 
 int refresh_count_hint(rspcl_ctx* ctx, const rspcl_cloud* c, std::vector<int>* counts_out) {
   std::vector<int> cnt(c->n_seg);
-  CU(ctx, cudaMemcpyAsync(cnt.data(), c->count, c->n_seg * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, small_d2h(ctx, cnt.data(), c->count, c->n_seg * sizeof(int)));
+  CU(ctx, ctx_sync(ctx));
   int m = 0;
   for (int v : cnt) m = v > m ? v : m;
   const_cast<rspcl_cloud*>(c)->max_count_hint = m;
@@ -731,7 +747,7 @@ extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rsp
   int* d_fc = nullptr;
   if (guess) {
     CU(ctx, scratch_alloc(ctx, &d_guess, (size_t)S * 16));
-    CU(ctx, cudaMemcpyAsync(d_guess, guess, (size_t)S * 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, small_h2d(ctx, d_guess, guess, (size_t)S * 16 * sizeof(float)));
   }
   if (first_corr) CU(ctx, scratch_alloc(ctx, &d_fc, (size_t)S * (src->stride ? src->stride : 1)));
   rc = icp_align_device(ctx, src, tgt, prm, d_guess, results, aligned, d_fc);
@@ -746,12 +762,12 @@ extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rsp
       int *d_off = nullptr, *packed = nullptr;
       CU(ctx, scratch_alloc(ctx, &d_off, (size_t)S));
       CU(ctx, scratch_alloc(ctx, &packed, (size_t)total));
-      CU(ctx, cudaMemcpyAsync(d_off, off.data(), S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      CU(ctx, small_h2d(ctx, d_off, off.data(), S * sizeof(int)));
       dim3 grid(blocks_per_seg(ctx, S, src->max_count_hint, 256), S);
       k_pack_i32<<<grid, 256, 0, ctx->stream>>>(d_fc, src->count, d_off, src->stride, packed);
       LAUNCH_CHECK(ctx);
-      CU(ctx, cudaMemcpyAsync(first_corr, packed, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(ctx, cudaStreamSynchronize(ctx->stream));
+      CU(ctx, small_d2h(ctx, first_corr, packed, (size_t)total * sizeof(int)));
+      CU(ctx, ctx_sync(ctx));
       scratch_free(ctx, d_off);
       scratch_free(ctx, packed);
     }

@@ -924,7 +924,7 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   CU(ctx, scratch_alloc(ctx, &partials, (size_t)S * nblk * NACC));
   CU(ctx, scratch_alloc(ctx, &n_active, 1));
   CU(ctx, scratch_alloc(ctx, &d_T, (size_t)S * 16));
-  CU(ctx, cudaMemcpyAsync(n_active, &S, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, small_h2d(ctx, n_active, &S, sizeof(int)));
   k_ndt_init<<<div_up(S, 64), 64, 0, ctx->stream>>>(st, ev, d_guess, S);
   LAUNCH_CHECK(ctx);
   NdtCtl ctl;
@@ -947,22 +947,23 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       LAUNCH_CHECK(ctx);
     }
     done_evals += chunk;
-    CU(ctx, cudaMemcpyAsync(&active, n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, small_d2h(ctx, &active, n_active, sizeof(int)));
+    CU(ctx, ctx_sync(ctx));
     if (chunk < 32) chunk *= 2;
   }
   std::vector<NdtState> hst(S);
   int range = 0;
-  CU(ctx, cudaMemcpyAsync(hst.data(), st, (size_t)S * sizeof(NdtState), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(&range, d_range, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, small_d2h(ctx, hst.data(), st, (size_t)S * sizeof(NdtState)));
+  CU(ctx, small_d2h(ctx, &range, d_range, sizeof(int)));
   if (aligned) {
     k_ndt_gather_T<<<div_up(S * 16, 256), 256, 0, ctx->stream>>>(st, d_T, S);
     LAUNCH_CHECK(ctx);
     rc = transform_device(ctx, src, d_T, 0, aligned);
   }
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, ctx_sync(ctx));
   std::vector<int> scnt(S);
-  CU(ctx, cudaMemcpy(scnt.data(), src->count, S * sizeof(int), cudaMemcpyDeviceToHost));
+  CU(ctx, small_d2h(ctx, scnt.data(), src->count, S * sizeof(int)));
+  CU(ctx, ctx_sync(ctx));
   for (int s = 0; s < S; ++s) {
     memcpy(h_results[s].T, hst[s].final_T, 64);
     h_results[s].converged = hst[s].converged;
@@ -996,7 +997,7 @@ extern "C" int rspcl_ndt_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rsp
   float* d_guess = nullptr;
   if (guess) {
     CU(ctx, scratch_alloc(ctx, &d_guess, (size_t)src->n_seg * 16));
-    CU(ctx, cudaMemcpyAsync(d_guess, guess, (size_t)src->n_seg * 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, small_h2d(ctx, d_guess, guess, (size_t)src->n_seg * 16 * sizeof(float)));
   }
   rc = ndt_align_device(ctx, src, tgt, prm, d_guess, results, aligned);
   scratch_free(ctx, d_guess);
@@ -1016,16 +1017,16 @@ extern "C" int rspcl_ndt_voxels(rspcl_ctx* ctx, const rspcl_cloud* tgt, const rs
   rc = ndt_grid_build(ctx, tgt, prm, &G, d_range);
   if (rc) return rc;
   int total = 0;
-  CU(ctx, cudaMemcpyAsync(&total, G.n_leaves, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(n_vox, G.nvox_seg, tgt->n_seg * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, small_d2h(ctx, &total, G.n_leaves, sizeof(int)));
+  CU(ctx, small_d2h(ctx, n_vox, G.nvox_seg, tgt->n_seg * sizeof(int)));
+  CU(ctx, ctx_sync(ctx));
   if (total > capacity) {
     ndt_grid_free(ctx, &G);
     scratch_free(ctx, d_range);
     RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "ndt_voxels: %d voxels, capacity %lld", total, capacity);
   }
-  if (total) CU(ctx, cudaMemcpyAsync(host_records, G.vox, (size_t)total * sizeof(VoxRec), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (total) CU(ctx, small_d2h(ctx, host_records, G.vox, (size_t)total * sizeof(VoxRec)));
+  CU(ctx, ctx_sync(ctx));
   ndt_grid_free(ctx, &G);
   scratch_free(ctx, d_range);
   return RSPCL_OK;
@@ -1056,7 +1057,7 @@ extern "C" int rspcl_ndt_derivatives(rspcl_ctx* ctx, const rspcl_cloud* src, con
   CU(ctx, scratch_alloc(ctx, &d_p, (size_t)S * 6));
   CU(ctx, scratch_alloc(ctx, &partials, (size_t)S * nblk * NACC));
   CU(ctx, scratch_alloc(ctx, &d_out, (size_t)S * NACC));
-  CU(ctx, cudaMemcpyAsync(d_p, p, (size_t)S * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, small_h2d(ctx, d_p, p, (size_t)S * 6 * sizeof(double)));
   k_ndt_eval_setup<<<div_up(S, 64), 64, 0, ctx->stream>>>(ev, d_p, S);
   LAUNCH_CHECK(ctx);
   k_ndt_eval<<<dim3(nblk, S), NT, 0, ctx->stream>>>(src->pts, src->count, src->stride, ev, G, d1, d2, partials);
@@ -1064,8 +1065,8 @@ extern "C" int rspcl_ndt_derivatives(rspcl_ctx* ctx, const rspcl_cloud* src, con
   k_ndt_sum_partials<<<S, 32, 0, ctx->stream>>>(partials, nblk, S, d_out);
   LAUNCH_CHECK(ctx);
   std::vector<double> out((size_t)S * NACC);
-  CU(ctx, cudaMemcpyAsync(out.data(), d_out, out.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, small_d2h(ctx, out.data(), d_out, out.size() * sizeof(double)));
+  CU(ctx, ctx_sync(ctx));
   for (int s = 0; s < S; ++s) {
     const double* o = &out[(size_t)s * NACC];
     score[s] = o[0];

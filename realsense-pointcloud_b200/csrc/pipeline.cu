@@ -112,8 +112,8 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
   int *d_src = nullptr, *d_tgt = nullptr;
   CU(ctx, scratch_alloc(ctx, &d_src, (size_t)n_pairs));
   CU(ctx, scratch_alloc(ctx, &d_tgt, (size_t)n_pairs));
-  CU(ctx, cudaMemcpyAsync(d_src, src_idx, n_pairs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(d_tgt, tgt_idx, n_pairs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, small_h2d(ctx, d_src, src_idx, n_pairs * sizeof(int)));
+  CU(ctx, small_h2d(ctx, d_tgt, tgt_idx, n_pairs * sizeof(int)));
   TmpCloud Sc(ctx), Tc(ctx), Ac(ctx);
   if (Sc.init(n_pairs, pstride) || Tc.init(n_pairs, pstride) || Ac.init(n_pairs, pstride))
     RSPCL_FAIL(ctx, RSPCL_ERR_CUDA, "register_pairs: scratch allocation failed");
@@ -127,7 +127,7 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
   float* d_guess = nullptr;
   if (guess) {
     CU(ctx, scratch_alloc(ctx, &d_guess, (size_t)n_pairs * 16));
-    CU(ctx, cudaMemcpyAsync(d_guess, guess, (size_t)n_pairs * 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, small_h2d(ctx, d_guess, guess, (size_t)n_pairs * 16 * sizeof(float)));
   }
   std::vector<float> hT((size_t)n_pairs * 32);
   std::vector<rspcl_icp_result> fine(n_pairs);
@@ -172,8 +172,8 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
     int* d_acc = nullptr;
     CU(ctx, scratch_alloc(ctx, &d_T, (size_t)n_pairs * 32));
     CU(ctx, scratch_alloc(ctx, &d_acc, (size_t)n_pairs));
-    CU(ctx, cudaMemcpyAsync(d_T, hT.data(), hT.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(d_acc, accept.data(), n_pairs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, small_h2d(ctx, d_T, hT.data(), hT.size() * sizeof(float)));
+    CU(ctx, small_h2d(ctx, d_acc, accept.data(), n_pairs * sizeof(int)));
     dim3 gt(blocks_per_seg(ctx, n_pairs, npx, 256), n_pairs);
     ProfScope prof(ctx, "k_transform2", (double)n_pairs * npx);
     k_transform2_gather<<<gt, 256, 0, ctx->stream>>>(frames->pts, npx, frames->stride, d_src, d_T, d_T + (size_t)n_pairs * 16,
@@ -183,7 +183,7 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
     out_transformed->width = frames->width;
     out_transformed->height = frames->height;
     out_transformed->max_count_hint = npx;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));  // hT / accept are host vectors about to go out of scope
+    CU(ctx, ctx_sync(ctx));  // hT / accept are host vectors about to go out of scope
     scratch_free(ctx, d_T);
     scratch_free(ctx, d_acc);
   }

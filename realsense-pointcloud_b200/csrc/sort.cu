@@ -102,8 +102,8 @@ int radix_sort_pairs(rspcl_ctx* ctx, unsigned long long* keys, int* vals, unsign
   k_digit_presence<<<pb, ST, 0, ctx->stream>>>(keys, n, d_presence);
   LAUNCH_CHECK(ctx);
   unsigned h_presence[8 * RADIX];
-  CU(ctx, cudaMemcpyAsync(h_presence, d_presence, sizeof(h_presence), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, small_d2h(ctx, h_presence, d_presence, sizeof(h_presence)));
+  CU(ctx, ctx_sync(ctx));
   scratch_free(ctx, d_presence);
   const int nblk = div_up(n, TILE);
   int* bh = nullptr;

@@ -264,8 +264,8 @@ int voxel_approx_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float leaf[
   }
   int over = 0;
   if (!alias && out->stride < in->max_count_hint) {
-    CU(ctx, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, small_d2h(ctx, &over, d_over, sizeof(int)));
+    CU(ctx, ctx_sync(ctx));
   }
   scratch_free(ctx, sorted);
   scratch_free(ctx, ev);
@@ -305,14 +305,14 @@ extern "C" int rspcl_voxel_keys(rspcl_ctx* ctx, const rspcl_cloud* in, const flo
   CU(ctx, scratch_alloc(ctx, &d_off, (size_t)in->n_seg + 1));
   CU(ctx, scratch_alloc(ctx, &d_ijk, (size_t)total * 3));
   CU(ctx, scratch_alloc(ctx, &d_slot, (size_t)total));
-  CU(ctx, cudaMemcpyAsync(d_off, off.data(), (in->n_seg + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, small_h2d(ctx, d_off, off.data(), (in->n_seg + 1) * sizeof(int)));
   const float3 inv = make_float3(1.0f / leaf[0], 1.0f / leaf[1], 1.0f / leaf[2]);
   dim3 grid(blocks_per_seg(ctx, in->n_seg, maxc, 256), in->n_seg);
   k_voxel_keys<<<grid, 256, 0, ctx->stream>>>(in->pts, in->count, d_off, in->stride, inv, d_ijk, d_slot);
   LAUNCH_CHECK(ctx);
-  CU(ctx, cudaMemcpyAsync(host_ijk, d_ijk, (size_t)total * 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(host_slot, d_slot, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, small_d2h(ctx, host_ijk, d_ijk, (size_t)total * 3 * sizeof(int)));
+  CU(ctx, small_d2h(ctx, host_slot, d_slot, (size_t)total * sizeof(int)));
+  CU(ctx, ctx_sync(ctx));
   scratch_free(ctx, d_off);
   scratch_free(ctx, d_ijk);
   scratch_free(ctx, d_slot);

@@ -60,7 +60,7 @@ NDT_VOXEL = np.dtype([("ijk", "<i4", 3), ("npts", "<i4"), ("centroid", "<f4", 3)
 
 EXPORTS = [
     "rspcl_ctx_create", "rspcl_ctx_destroy", "rspcl_last_error", "rspcl_ctx_sync", "rspcl_timer_start",
-    "rspcl_timer_stop", "rspcl_launch_count", "rspcl_profile_enable", "rspcl_profile_reset", "rspcl_profile_get", "rspcl_host_alloc", "rspcl_host_free", "rspcl_cloud_create",
+    "rspcl_timer_stop", "rspcl_timer_mark", "rspcl_timer_span", "rspcl_launch_count", "rspcl_profile_enable", "rspcl_profile_reset", "rspcl_profile_get", "rspcl_host_alloc", "rspcl_host_free", "rspcl_cloud_create",
     "rspcl_cloud_destroy", "rspcl_cloud_n_seg", "rspcl_cloud_stride", "rspcl_cloud_dims", "rspcl_cloud_upload",
     "rspcl_cloud_counts", "rspcl_cloud_download", "rspcl_crop35", "rspcl_edge_extract", "rspcl_voxel_approx",
     "rspcl_voxel_keys", "rspcl_transform", "rspcl_concat", "rspcl_cloud_copy_segment", "rspcl_icp_reference_params",
@@ -136,6 +136,13 @@ def from_pcl32(p):
     return out
 
 
+def timer_span(ctxs):
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    ms = C.c_float()
+    ctxs[0].check(lib().rspcl_timer_span(arr, len(ctxs), C.byref(ms)))
+    return ms.value
+
+
 def icp_params(**kw):
     p = IcpParams()
     lib().rspcl_icp_reference_params(C.byref(p))
@@ -177,6 +184,9 @@ class Context:
         ms = C.c_float()
         self.check(lib().rspcl_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def timer_mark(self):
+        self.check(lib().rspcl_timer_mark(self.h))
 
     def launches(self):
         return lib().rspcl_launch_count(self.h)
