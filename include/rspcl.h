@@ -188,6 +188,22 @@ int rspcl_ndt_voxels(rspcl_ctx* ctx, const rspcl_cloud* tgt, const rspcl_ndt_par
 int rspcl_ndt_derivatives(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt,
                           const rspcl_ndt_params* prm, const double* p, double* score, double* g, double* H);
 
+/* ------------------------------------------------------------------ point-sharded multi-GPU mode
+ * One process per GPU.  Every rank passes its SHARD of the source points and a full replica of the target; the
+ * per-iteration partial sums {n, sum s, sum t, sum s t^T, sum d^2} (17 fp64, ICP) / {score, g, H} (28 fp64, NDT) are
+ * combined with an NCCL all-reduce on the context stream and every rank runs the identical solve, so all ranks return
+ * the same transform / convergence state (n_corr is the global count).  `aligned` receives the rank's shard moved by
+ * the final transform.  These calls are collective: every rank of the communicator must make them in the same order.
+ * rspcl_comm_unique_id is called on one rank and the 128 bytes are distributed by the application (e.g.
+ * torch.distributed broadcast, MPI). */
+int rspcl_comm_unique_id(void* id128);
+int rspcl_comm_init(rspcl_ctx* ctx, int nranks, int rank, const void* id128);
+int rspcl_comm_destroy(rspcl_ctx* ctx);
+int rspcl_icp_align_sharded(rspcl_ctx* ctx, const rspcl_cloud* src_shard, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
+                            const float* guess, rspcl_icp_result* results, rspcl_cloud* aligned);
+int rspcl_ndt_align_sharded(rspcl_ctx* ctx, const rspcl_cloud* src_shard, const rspcl_cloud* tgt, const rspcl_ndt_params* prm,
+                            const float* guess, rspcl_ndt_result* results, rspcl_cloud* aligned);
+
 /* ------------------------------------------------------------------ pairwise registration pipeline
  * One call = the reference's per-frame body (icp:75-120 / ndt:68-108) for a batch of independent frame pairs
  * (SURVEY H5 pairwise formulation): edges of every frame once, 1 cm approximate voxel filter, coarse stage (ICP or

@@ -27,6 +27,10 @@ struct rspcl_ctx {
   size_t z_cap = 0, z_used = 0;
   struct ZPending { void* dst; const void* src; size_t n; void* owned; };  // owned: pinned bounce buffer to free
   std::vector<ZPending> z_pending;
+  // point-sharded mode (comm.cu)
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+  bool sharded_call = false;  // set for the duration of a *_sharded entry point
   // optional per-kernel event profile
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int kernel; double units; };
@@ -120,6 +124,7 @@ int ensure_stage(rspcl_ctx* ctx, size_t bytes);
 cudaError_t small_h2d(rspcl_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 cudaError_t small_d2h(rspcl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);  // valid after ctx_sync()
 cudaError_t ctx_sync(rspcl_ctx* ctx);
+int comm_allreduce_f64(rspcl_ctx* ctx, double* buf, size_t n);
 int blocks_per_seg(const rspcl_ctx* ctx, int n_seg, int max_count, int threads);
 int transform_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float* d_T, int broadcast, rspcl_cloud* out);
 int ensure_gray(rspcl_ctx* ctx, rspcl_cloud* c);

@@ -412,6 +412,20 @@ __global__ void __launch_bounds__(IT) k_icp_step(float4* __restrict__ work, cons
   }
 }
 
+// point-sharded mode: CTA partials -> per-pair totals (then all-reduced across ranks before the solve)
+__global__ void k_icp_sum_partials(const double* __restrict__ partials, int nblk, const IcpState* __restrict__ st,
+                                   double* __restrict__ totals) {
+  const int seg = blockIdx.x, lane = threadIdx.x;
+  if (lane >= NRED) return;
+  double v = 0;
+  // finished pairs contribute zeros on every rank (their k_icp_step exits early and leaves stale partials)
+  if (!st[seg].done) {
+    const double* P = partials + (size_t)seg * nblk * NRED + lane;
+    for (int b = 0; b < nblk; ++b) v += P[(size_t)b * NRED];
+  }
+  totals[seg * NRED + lane] = v;
+}
+
 // K5b: one warp per pair combines the CTA partials in block order (deterministic) and runs the solve
 __global__ void __launch_bounds__(32) k_icp_solve(IcpState* __restrict__ st, const double* __restrict__ partials, int nblk,
                                                   IcpDevParams prm, int* __restrict__ n_active) {
@@ -555,9 +569,12 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
 
   // ---- persistent shared-memory path: one cluster per pair, all iterations in one launch (icp_persist.cuh)
   bool persist_done = false;
+  const bool sharded = ctx->sharded_call && ctx->nccl_comm && ctx->nranks > 1;
+  double* totals = nullptr;
+  if (sharded) CU(ctx, scratch_alloc(ctx, &totals, (size_t)S * NRED));
   {
     const char* env = getenv("RSPCL_ICP_PERSIST");
-    const bool want = !(env && env[0] == '0');
+    const bool want = !(env && env[0] == '0') && !sharded;
     if (want && !brute && tgt->max_count_hint <= P_NTMAX && src->max_count_hint > 0 && src->max_count_hint < 65536) {
       int* d_status = nullptr;
       CU(ctx, scratch_alloc(ctx, &d_status, (size_t)S));
@@ -678,7 +695,16 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         LAUNCH_CHECK(ctx);
       }
       ProfScope prof2(ctx, "k_icp_solve", (double)S);
-      k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, partials, nblk, dp, n_active);
+      if (sharded) {
+        // partial sums of this rank's shard -> NCCL all-reduce over NVLink -> identical solve on every rank
+        k_icp_sum_partials<<<S, 32, 0, ctx->stream>>>(partials, nblk, st, totals);
+        LAUNCH_CHECK(ctx);
+        int rcc = comm_allreduce_f64(ctx, totals, (size_t)S * NRED);
+        if (rcc) return rcc;
+        k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, totals, 1, dp, n_active);
+      } else {
+        k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, partials, nblk, dp, n_active);
+      }
       LAUNCH_CHECK(ctx);
     }
     done_iters += todo;
@@ -716,6 +742,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   scratch_free(ctx, n_active);
   scratch_free(ctx, d_range);
   scratch_free(ctx, d_T);
+  scratch_free(ctx, totals);
   if (rc) return rc;
   if (range) RSPCL_FAIL(ctx, RSPCL_ERR_RANGE, "icp_align: target coordinates exceed the grid key range (+-32767 cells of %g m)", cs);
   return RSPCL_OK;
@@ -774,5 +801,15 @@ extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rsp
   }
   scratch_free(ctx, d_guess);
   scratch_free(ctx, d_fc);
+  return rc;
+}
+
+extern "C" int rspcl_icp_align_sharded(rspcl_ctx* ctx, const rspcl_cloud* src_shard, const rspcl_cloud* tgt,
+                                       const rspcl_icp_params* prm, const float* guess, rspcl_icp_result* results,
+                                       rspcl_cloud* aligned) {
+  if (!ctx) return RSPCL_ERR_ARG;
+  ctx->sharded_call = true;
+  const int rc = rspcl_icp_align(ctx, src_shard, tgt, prm, guess, results, aligned, nullptr);
+  ctx->sharded_call = false;
   return rc;
 }

@@ -787,6 +787,17 @@ __global__ void k_ndt_eval_setup(NdtEval* __restrict__ ev, const double* __restr
   E->pad = 0;
 }
 
+// point-sharded mode: per-pair totals of this rank's shard (zeros for finished pairs), all-reduced before the controller
+__global__ void k_ndt_sum_partials_active(const double* __restrict__ partials, int nblk, const NdtEval* __restrict__ ev,
+                                          double* __restrict__ totals) {
+  const int seg = blockIdx.x, lane = threadIdx.x;
+  if (lane >= NACC) return;
+  double v = 0;
+  if (ev[seg].active)
+    for (int b = 0; b < nblk; ++b) v += partials[((size_t)seg * nblk + b) * NACC + lane];
+  totals[seg * NACC + lane] = v;
+}
+
 __global__ void k_ndt_sum_partials(const double* __restrict__ partials, int nblk, int n_seg, double* __restrict__ out) {
   const int seg = blockIdx.x, lane = threadIdx.x;
   if (lane >= NACC) return;
@@ -924,6 +935,9 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   CU(ctx, scratch_alloc(ctx, &partials, (size_t)S * nblk * NACC));
   CU(ctx, scratch_alloc(ctx, &n_active, 1));
   CU(ctx, scratch_alloc(ctx, &d_T, (size_t)S * 16));
+  const bool sharded = ctx->sharded_call && ctx->nccl_comm && ctx->nranks > 1;
+  double* totals = nullptr;
+  if (sharded) CU(ctx, scratch_alloc(ctx, &totals, (size_t)S * NACC));
   CU(ctx, small_h2d(ctx, n_active, &S, sizeof(int)));
   k_ndt_init<<<div_up(S, 64), 64, 0, ctx->stream>>>(st, ev, d_guess, S);
   LAUNCH_CHECK(ctx);
@@ -943,7 +957,15 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         k_ndt_eval<<<ge, NT, 0, ctx->stream>>>(src->pts, src->count, src->stride, ev, G, d1, d2, partials);
         LAUNCH_CHECK(ctx);
       }
-      k_ndt_control<<<S, 32, 0, ctx->stream>>>(st, ev, partials, nblk, ctl, n_active);
+      if (sharded) {
+        k_ndt_sum_partials_active<<<S, 32, 0, ctx->stream>>>(partials, nblk, ev, totals);
+        LAUNCH_CHECK(ctx);
+        int rcc = comm_allreduce_f64(ctx, totals, (size_t)S * NACC);
+        if (rcc) return rcc;
+        k_ndt_control<<<S, 32, 0, ctx->stream>>>(st, ev, totals, 1, ctl, n_active);
+      } else {
+        k_ndt_control<<<S, 32, 0, ctx->stream>>>(st, ev, partials, nblk, ctl, n_active);
+      }
       LAUNCH_CHECK(ctx);
     }
     done_evals += chunk;
@@ -981,6 +1003,7 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   scratch_free(ctx, n_active);
   scratch_free(ctx, d_T);
   scratch_free(ctx, d_range);
+  scratch_free(ctx, totals);
   if (rc) return rc;
   if (range) RSPCL_FAIL(ctx, RSPCL_ERR_RANGE, "ndt_align: target coordinates exceed the voxel key range");
   return RSPCL_OK;
@@ -1086,4 +1109,14 @@ extern "C" int rspcl_ndt_derivatives(rspcl_ctx* ctx, const rspcl_cloud* src, con
   scratch_free(ctx, d_out);
   scratch_free(ctx, d_range);
   return RSPCL_OK;
+}
+
+extern "C" int rspcl_ndt_align_sharded(rspcl_ctx* ctx, const rspcl_cloud* src_shard, const rspcl_cloud* tgt,
+                                       const rspcl_ndt_params* prm, const float* guess, rspcl_ndt_result* results,
+                                       rspcl_cloud* aligned) {
+  if (!ctx) return RSPCL_ERR_ARG;
+  ctx->sharded_call = true;
+  const int rc = rspcl_ndt_align(ctx, src_shard, tgt, prm, guess, results, aligned);
+  ctx->sharded_call = false;
+  return rc;
 }

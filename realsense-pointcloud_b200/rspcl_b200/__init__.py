@@ -65,7 +65,8 @@ EXPORTS = [
     "rspcl_cloud_counts", "rspcl_cloud_download", "rspcl_crop35", "rspcl_edge_extract", "rspcl_voxel_approx",
     "rspcl_voxel_keys", "rspcl_transform", "rspcl_concat", "rspcl_cloud_copy_segment", "rspcl_icp_reference_params",
     "rspcl_icp_align", "rspcl_fitness", "rspcl_nearest", "rspcl_ndt_reference_params", "rspcl_ndt_align",
-    "rspcl_ndt_voxels", "rspcl_ndt_derivatives", "rspcl_register_pairs",
+    "rspcl_ndt_voxels", "rspcl_ndt_derivatives", "rspcl_register_pairs", "rspcl_comm_unique_id", "rspcl_comm_init",
+    "rspcl_comm_destroy", "rspcl_icp_align_sharded", "rspcl_ndt_align_sharded",
 ]
 
 _lib = None
@@ -415,3 +416,47 @@ def register_pairs(ctx, frames, src_idx, tgt_idx, coarse=COARSE_ICP, icp=None, n
                                          _p(lf), C.c_float(t_low), C.c_float(t_high), _p(g), res,
                                          out_transformed.h if out_transformed is not None else None))
     return res
+
+
+# -------------------------------------------------------------------- point-sharded multi-GPU mode
+def comm_unique_id():
+    buf = np.zeros(128, np.uint8)
+    rc = lib().rspcl_comm_unique_id(_p(buf))
+    if rc != 0:
+        raise RspclError("rspcl_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf
+
+
+def comm_init(ctx, nranks, rank, unique_id):
+    uid = np.ascontiguousarray(unique_id, np.uint8)
+    ctx.check(lib().rspcl_comm_init(ctx.h, int(nranks), int(rank), _p(uid)))
+
+
+def comm_destroy(ctx):
+    ctx.check(lib().rspcl_comm_destroy(ctx.h))
+
+
+def icp_align_sharded(ctx, src_shard, tgt, prm=None, guess=None, want_aligned=False):
+    prm = prm or icp_params()
+    S = src_shard.n_seg
+    res = (IcpResult * S)()
+    for s in range(S):
+        res[s].prev_mse = DBL_MAX
+    g = mats_to_c(guess, S) if guess is not None else None
+    aligned = Cloud(ctx, S, src_shard.stride) if want_aligned else None
+    ctx.check(lib().rspcl_icp_align_sharded(ctx.h, src_shard.h, tgt.h, C.byref(prm), _p(g), res, aligned.h if aligned else None))
+    out = [{"T": c_to_mat(r.T), "converged": bool(r.converged), "state": r.state, "iterations": r.iterations,
+            "n_corr": r.n_corr, "mse": r.mse} for r in res]
+    return out, aligned
+
+
+def ndt_align_sharded(ctx, src_shard, tgt, prm=None, guess=None, want_aligned=False):
+    prm = prm or ndt_params()
+    S = src_shard.n_seg
+    res = (NdtResult * S)()
+    g = mats_to_c(guess, S) if guess is not None else None
+    aligned = Cloud(ctx, S, src_shard.stride) if want_aligned else None
+    ctx.check(lib().rspcl_ndt_align_sharded(ctx.h, src_shard.h, tgt.h, C.byref(prm), _p(g), res, aligned.h if aligned else None))
+    out = [{"T": c_to_mat(r.T), "converged": bool(r.converged), "iterations": r.iterations, "score": r.score,
+            "n_derivative_evals": r.n_derivative_evals, "trans_probability": r.trans_probability} for r in res]
+    return out, aligned

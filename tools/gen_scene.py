@@ -151,6 +151,31 @@ class Scene:
         return pts
 
 
+def sample_room_surface(seed, n, chunk=4_000_000):
+    """n points uniformly sampled on the inner surface of the 5 x 3 x 4 m room (area-weighted over the six faces),
+    as a POINT array -- the dense single-cloud input of the point-sharded configuration (BASELINE configs[4])."""
+    rng = np.random.default_rng(seed)
+    lo = np.array([-2.5, -1.5, -2.0])
+    hi = np.array([2.5, 1.5, 2.0])
+    ext = hi - lo
+    areas = np.array([ext[1] * ext[2]] * 2 + [ext[0] * ext[2]] * 2 + [ext[0] * ext[1]] * 2)
+    out = np.zeros(n, POINT)
+    done = 0
+    while done < n:
+        m = min(chunk, n - done)
+        face = rng.choice(6, size=m, p=areas / areas.sum())
+        p = lo + rng.random((m, 3)) * ext
+        axis = face // 2
+        side = face % 2
+        p[np.arange(m), axis] = np.where(side == 1, hi[axis], lo[axis])
+        out["x"][done:done + m] = p[:, 0]
+        out["y"][done:done + m] = p[:, 1]
+        out["z"][done:done + m] = p[:, 2]
+        out["rgba"][done:done + m] = (np.uint32(255) << 24) | (face.astype(np.uint32) * np.uint32(0x202020) + np.uint32(0x303030))
+        done += m
+    return out
+
+
 def make_sweep(seed, n_frames, w=640, h=480, rads=-0.523599, max_rot_deg=0.08, max_trans=0.003, noise_scale=0.0):
     """Returns (frames [n, w*h] POINT, T_gt [n,4,4] float64 with X_0 = T_k X_k)."""
     rng = np.random.default_rng(seed)
