@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(IT) k_icp_step(float4* __restrict__ work, cons
       j = grid_nn_bounded(g, seg, p.x, p.y, p.z, prm.search_r, &d2, &t);
     }
     const bool ok = (i < n) && j >= 0 && !((double)d2 > prm.max_dist_sqr);
-    if (want_corr && i < n) first_corr[(size_t)seg * stride + i] = ok ? j : -1;
+    if (want_corr && i < n) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = ok ? j : -1;  // .w = original index
     if (ok) {
       const double sx = p.x, sy = p.y, sz = p.z, tx = t.x, ty = t.y, tz = t.z;
       acc[0] += 1.0;
@@ -564,8 +564,31 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, S);
   LAUNCH_CHECK(ctx);
   dim3 gcopy(blocks_per_seg(ctx, S, src->max_count_hint, 256), S);
-  k_copy_work<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, work, wstride);
-  LAUNCH_CHECK(ctx);
+  // Working cloud = source in SPATIAL order (radix sort by cell key), original index kept in .w: neighbouring lanes
+  // then probe neighbouring cells (coalesced / cached probes, far less divergence).  Sums are order-independent up to
+  // fp64 rounding; first_corr and the aligned output are written in original order.
+  const float sort_inv_cs = brute ? 10.0f : 1.0f / (float)(prm->max_corr_dist * 4.1);
+  int* perm = nullptr;
+  const int pstride = src->max_count_hint > 0 ? src->max_count_hint : 1;
+  {
+    const long long N = (long long)S * pstride;
+    unsigned long long *keys = nullptr, *tkeys = nullptr;
+    int* tvals = nullptr;
+    CU(ctx, scratch_alloc(ctx, &keys, (size_t)N));
+    CU(ctx, scratch_alloc(ctx, &tkeys, (size_t)N));
+    CU(ctx, scratch_alloc(ctx, &perm, (size_t)N));
+    CU(ctx, scratch_alloc(ctx, &tvals, (size_t)N));
+    dim3 gk(blocks_per_seg(ctx, S, pstride, 256), S);
+    k_source_keys<<<gk, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, pstride, sort_inv_cs, keys, perm);
+    LAUNCH_CHECK(ctx);
+    int rcs = radix_sort_pairs(ctx, keys, perm, tkeys, tvals, N);
+    if (rcs) return rcs;
+    k_copy_work_perm<<<gk, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, perm, pstride, work, wstride);
+    LAUNCH_CHECK(ctx);
+    scratch_free(ctx, keys);
+    scratch_free(ctx, tkeys);
+    scratch_free(ctx, tvals);
+  }
 
   // ---- persistent shared-memory path: one cluster per pair, all iterations in one launch (icp_persist.cuh)
   bool persist_done = false;
@@ -581,27 +604,6 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       CU(ctx, cudaMemsetAsync(d_status, 0, (size_t)S * sizeof(int), ctx->stream));
       const int cl = (4 * S <= ctx->sm_count) ? 4 : ((2 * S <= ctx->sm_count) ? 2 : 1);
       const float inv_cs_p = 1.0f / (float)(prm->max_corr_dist * 4.1);
-      {  // spatially sorted working cloud
-        const int pstride = src->max_count_hint;
-        const long long N = (long long)S * pstride;
-        unsigned long long *keys = nullptr, *tkeys = nullptr;
-        int *vals = nullptr, *tvals = nullptr;
-        CU(ctx, scratch_alloc(ctx, &keys, (size_t)N));
-        CU(ctx, scratch_alloc(ctx, &tkeys, (size_t)N));
-        CU(ctx, scratch_alloc(ctx, &vals, (size_t)N));
-        CU(ctx, scratch_alloc(ctx, &tvals, (size_t)N));
-        dim3 gk(blocks_per_seg(ctx, S, pstride, 256), S);
-        k_source_keys<<<gk, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, pstride, inv_cs_p, keys, vals);
-        LAUNCH_CHECK(ctx);
-        int rcs = radix_sort_pairs(ctx, keys, vals, tkeys, tvals, N);
-        if (rcs) return rcs;
-        k_copy_work_perm<<<gk, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, vals, pstride, work, wstride);
-        LAUNCH_CHECK(ctx);
-        scratch_free(ctx, keys);
-        scratch_free(ctx, tkeys);
-        scratch_free(ctx, vals);
-        scratch_free(ctx, tvals);
-      }
       static bool attr_set = false;
       if (!attr_set) {
         CU(ctx, cudaFuncSetAttribute(k_icp_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
@@ -656,7 +658,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       } else {  // a target did not fit the shared-memory grid: redo the whole batch on the global-memory path
         k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, S);
         LAUNCH_CHECK(ctx);
-        k_copy_work<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, work, wstride);
+        k_copy_work_perm<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, perm, pstride, work, wstride);
         LAUNCH_CHECK(ctx);
       }
     }
@@ -743,6 +745,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   scratch_free(ctx, d_range);
   scratch_free(ctx, d_T);
   scratch_free(ctx, totals);
+  scratch_free(ctx, perm);
   if (rc) return rc;
   if (range) RSPCL_FAIL(ctx, RSPCL_ERR_RANGE, "icp_align: target coordinates exceed the grid key range (+-32767 cells of %g m)", cs);
   return RSPCL_OK;
