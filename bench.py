@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=33, help="frames per GPU sweep (pairs = frames - 1)")
+    ap.add_argument("--frames", type=int, default=65, help="frames per GPU sweep (pairs = frames - 1); 65 = a 64-pair sweep (configs[3])")
     ap.add_argument("--iters", type=int, default=50, help="forced ICP iterations per stage (configs[1]: 50)")
     ap.add_argument("--coarse", default="icp", choices=["icp", "ndt"])
     ap.add_argument("--seed", type=int, default=2)
@@ -357,7 +357,9 @@ def main():
     chk = R.from_pcl32(out_rows[0])
     download()
     ref0 = R.from_pcl32(h_out.view(R.PCL32).reshape(n_pairs, NPX)[0])
-    assert np.array_equal(chk, ref0), "pipelined e2e result differs from the single-context result"
+    # (bit equality is not guaranteed: the cluster size, hence the fp64 summation order, depends on the batch size)
+    dmax = max(float(np.abs(chk[a_] - ref0[a_]).max()) for a_ in "xyz")
+    assert dmax < 1e-5 and np.array_equal(chk["rgba"], ref0["rgba"]), "pipelined e2e result differs from the single-context result"
 
     # ---- roofline of the dominant kernel, from per-launch CUDA events in one extra profiled step
     ctx.profile_reset()

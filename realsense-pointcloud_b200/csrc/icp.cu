@@ -22,6 +22,7 @@ namespace cg = cooperative_groups;
 #include <math.h>
 #include <limits.h>
 #include <stdlib.h>
+#include <algorithm>
 
 namespace {
 
@@ -602,7 +603,30 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       int* d_status = nullptr;
       CU(ctx, scratch_alloc(ctx, &d_status, (size_t)S));
       CU(ctx, cudaMemsetAsync(d_status, 0, (size_t)S * sizeof(int), ctx->stream));
-      const int cl = (4 * S <= ctx->sm_count) ? 4 : ((2 * S <= ctx->sm_count) ? 2 : 1);
+      // pairs in decreasing size (longest-processing-time-first) and a cluster size from a small cost model:
+      // t(CL) ~ 0.7 * 4/CL + 0.3 per pair (point loop scales with 1/CL, solve + barriers do not), slots = SMs / CL
+      std::vector<int> hcnt(S), order(S);
+      CU(ctx, small_d2h(ctx, hcnt.data(), src->count, (size_t)S * sizeof(int)));
+      CU(ctx, ctx_sync(ctx));
+      for (int s = 0; s < S; ++s) order[s] = s;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hcnt[a] > hcnt[b]; });
+      int cl = 1;
+      {
+        double best = 1e30;
+        const int cands[3] = {4, 2, 1};
+        for (int c : cands) {
+          const double slots = (double)(ctx->sm_count / c) * (c == 4 ? 0.9 : 1.0);  // clusters of 4 do not tile every GPC
+          const double waves = (double)S / slots;
+          const double est = (0.7 * 4.0 / c + 0.3) * (waves > 1.0 ? waves : 1.0);
+          if (est < best) {
+            best = est;
+            cl = c;
+          }
+        }
+      }
+      int* d_order = nullptr;
+      CU(ctx, scratch_alloc(ctx, &d_order, (size_t)S));
+      CU(ctx, small_h2d(ctx, d_order, order.data(), (size_t)S * sizeof(int)));
       const float inv_cs_p = 1.0f / (float)(prm->max_corr_dist * 4.1);
       static bool attr_set = false;
       if (!attr_set) {
@@ -630,11 +654,11 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       ProfScope prof(ctx, "k_icp_persist", 0.0);
       cudaError_t le;
       if (cl == 4)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order);
       else if (cl == 2)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order);
       else
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order);
       CU(ctx, le);
       LAUNCH_CHECK(ctx);
       prof.end();
@@ -646,6 +670,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       CU(ctx, small_d2h(ctx, hc.data(), src->count, (size_t)S * sizeof(int)));
       CU(ctx, ctx_sync(ctx));
       scratch_free(ctx, d_status);
+      scratch_free(ctx, d_order);
       bool fallback = false;
       double units = 0;
       for (int s = 0; s < S; ++s) {

@@ -48,11 +48,12 @@ template <int CL>
 __global__ void __launch_bounds__(P_THREADS, 1)
 k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstride, IcpState* __restrict__ st_g,
               const float4* __restrict__ tgt, const int* __restrict__ tcount, int tstride, int shared_target,
-              IcpDevParams prm, float inv_cs, int* __restrict__ first_corr, int* __restrict__ status) {
+              IcpDevParams prm, float inv_cs, int* __restrict__ first_corr, int* __restrict__ status,
+              const int* __restrict__ order) {
   extern __shared__ __align__(16) unsigned char p_smem_raw[];
   PersistSmem& S = *reinterpret_cast<PersistSmem*>(p_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int pair = blockIdx.x / CL;
+  const int pair = order[blockIdx.x / CL];  // largest pairs first: later waves fill the gaps (LPT)
   const int crank = (CL > 1) ? (int)cg::this_cluster().block_rank() : 0;
   const int tseg = shared_target ? 0 : pair;
   const int nt = tcount[tseg];
