@@ -146,3 +146,36 @@ def test_register_pairs_ndt_coarse_matches_oracle(ctx, sweep3):
         for key in ("T_coarse", "T_fine"):
             ang, tr = pose_err(R.c_to_mat(getattr(res[i], key)), o[key])
             assert ang < 1e-4 and tr < 1e-4, (i, key, ang, tr)
+
+
+def test_config3_1280x720_ndt_005_voxels(ctx):
+    """BASELINE configs[2]: edge-based NDT on a 1280x720 pair (921,600 points per frame), 0.05 m voxels."""
+    W2, H2 = 1280, 720
+    fr, Tgt = gen_scene.make_sweep(3, 2, W2, H2, noise_scale=0.2)
+    frames = ctx.upload(list(fr), W2, H2)
+    edges, mask = R.edge_extract(ctx, frames, want_mask=True)
+    ec = []
+    for k in range(2):
+        m, near = orc.canny(fr[k], W2, H2)
+        assert near == 0 and np.array_equal(mask[k], m)
+        ec.append(orc.approx_voxel(orc.extract_edges(fr[k], W2, H2)[0]))
+    vox = R.voxel_approx(ctx, edges).download()
+    for k in range(2):
+        assert np.array_equal(vox[k].view(np.uint32), ec[k].view(np.uint32))
+    guess = np.eye(4)
+    guess[:3, :3] = gen_scene.rot_y(-0.523599)
+    kw = dict(resolution=0.05)
+    go = orc.NdtGrid(ec[0], orc.ndt_params(**kw)).voxels()
+    gg = R.ndt_voxels(ctx, ctx.upload([ec[0]]), R.ndt_params(**kw))[0]
+    assert len(gg) == len(go) > 100 and np.array_equal(gg["ijk"], go["ijk"]) and np.array_equal(gg["mean"], go["mean"])
+    p0 = orc.matrix_to_pose(guess)
+    s, g, Hm = R.ndt_derivatives(ctx, ctx.upload([ec[1]]), ctx.upload([ec[0]]), p0, R.ndt_params(**kw))
+    so, gr, Ho, _ = orc.NdtGrid(ec[0], orc.ndt_params(**kw)).derivatives(ec[1], p0)
+    assert abs(s[0] - so) <= 1e-6 * max(abs(so), 1.0)
+    assert np.allclose(g[0], gr, rtol=1e-5, atol=1e-6 * max(np.abs(gr).max(), 1.0))
+    assert np.allclose(Hm[0], Ho, rtol=1e-5, atol=1e-6 * max(np.abs(Ho).max(), 1.0))
+    res, _ = R.ndt_align(ctx, ctx.upload([ec[1]]), ctx.upload([ec[0]]), R.ndt_params(**kw), guess=guess, want_aligned=False)
+    o = orc.ndt_align(ec[1], ec[0], orc.ndt_params(**kw), guess=guess)
+    assert res[0]["converged"] == o["converged"] and res[0]["iterations"] == o["iterations"]
+    ang, tr = pose_err(res[0]["T"], o["T"])
+    assert ang < 1e-4 and tr < 1e-4, (ang, tr)

@@ -351,3 +351,49 @@ def test_register_pairs_reference_literal_settings(ctx, sweep3):
             ang, tr = pose_err(R.c_to_mat(getattr(res[i], key)), o[key])
             assert ang < 1e-4 and tr < 1e-4
         assert res[i].n_corr == o["fine"].n_corr
+
+
+def test_frames_with_holes_and_nans(ctx, pair2):
+    """librealsense emits (0,0,0) for missing depth and PCL clouds may carry NaNs: edges depend on rgb only,
+    the voxel filter bins the zero points into one voxel, non-finite points never become correspondences."""
+    fr, _ = pair2
+    rng = np.random.default_rng(23)
+    f = [fr[0].copy(), fr[1].copy()]
+    for c in f:
+        holes = rng.random(len(c)) < 0.05
+        c["x"][holes] = 0.0
+        c["y"][holes] = 0.0
+        c["z"][holes] = 0.0
+    nan_idx = rng.choice(len(f[1]), 2000, replace=False)
+    f[1]["z"][nan_idx] = np.nan
+    frames = ctx.upload(f, W, H)
+    edges, mask = R.edge_extract(ctx, frames, want_mask=True)
+    got = edges.download()
+    ec = []
+    for k in range(2):
+        m, _ = orc.canny(f[k], W, H)
+        assert np.array_equal(mask[k], m)
+        e, _ = orc.extract_edges(f[k], W, H)
+        assert np.array_equal(got[k].view(np.uint32), e.view(np.uint32))
+        ec.append(e)
+    # voxel filter on the finite part (NaN -> int conversion is undefined behaviour in the reference; the GPU and the
+    # oracle both use the x86 result, checked here on the hole-only frame)
+    v = R.voxel_approx(ctx, ctx.upload([ec[0]])).download()[0]
+    assert np.array_equal(v.view(np.uint32), orc.approx_voxel(ec[0]).view(np.uint32))
+    vn = R.voxel_approx(ctx, ctx.upload([ec[1]])).download()[0]
+    on = orc.approx_voxel(ec[1])
+    assert len(vn) == len(on)
+    for a in "xyz":  # NaN centroids appear at the same places (their payload bits are not comparable); the rest is bit-equal
+        nan_g, nan_o = np.isnan(vn[a]), np.isnan(on[a])
+        assert np.array_equal(nan_g, nan_o)
+        assert np.array_equal(vn[a][~nan_o].view(np.uint32), on[a][~nan_o].view(np.uint32))
+    assert np.array_equal(vn["rgba"], on["rgba"]) and np.isnan(on["z"]).sum() > 0
+    guess = np.eye(4)
+    guess[:3, :3] = gen_scene.rot_y(-0.523599)
+    res, aligned, fc = R.icp_align(ctx, ctx.upload([on]), ctx.upload([orc.approx_voxel(ec[0])]), R.icp_params(), guess=guess,
+                                   want_first_corr=True)
+    o = orc.icp_align(on, orc.approx_voxel(ec[0]), orc.icp_params(), guess=guess, want_first_corr=True)
+    assert np.array_equal(fc, o["first_corr"])
+    assert res[0]["n_corr"] == o["n_corr"] and res[0]["converged"] == o["converged"]
+    ang, tr = pose_err(res[0]["T"], o["T"])
+    assert ang < 1e-4 and tr < 1e-4
