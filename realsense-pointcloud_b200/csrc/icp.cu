@@ -625,6 +625,9 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         }
       }
       int* d_order = nullptr;
+      float* d_lb = nullptr;  // per-point certified lower bound of the distance to every non-cached target point
+      CU(ctx, scratch_alloc(ctx, &d_lb, (size_t)S * wstride));
+      CU(ctx, cudaMemsetAsync(d_lb, 0, (size_t)S * wstride * sizeof(float), ctx->stream));
       CU(ctx, scratch_alloc(ctx, &d_order, (size_t)S));
       CU(ctx, small_h2d(ctx, d_order, order.data(), (size_t)S * sizeof(int)));
       const float inv_cs_p = 1.0f / (float)(prm->max_corr_dist * 4.1);
@@ -654,11 +657,11 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       ProfScope prof(ctx, "k_icp_persist", 0.0);
       cudaError_t le;
       if (cl == 4)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb);
       else if (cl == 2)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb);
       else
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb);
       CU(ctx, le);
       LAUNCH_CHECK(ctx);
       prof.end();
@@ -671,6 +674,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       CU(ctx, ctx_sync(ctx));
       scratch_free(ctx, d_status);
       scratch_free(ctx, d_order);
+      scratch_free(ctx, d_lb);
       bool fallback = false;
       double units = 0;
       for (int s = 0; s < S; ++s) {

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstride, IcpState* __restrict__ st_g,
               const float4* __restrict__ tgt, const int* __restrict__ tcount, int tstride, int shared_target,
               IcpDevParams prm, float inv_cs, int* __restrict__ first_corr, int* __restrict__ status,
-              const int* __restrict__ order) {
+              const int* __restrict__ order, float* __restrict__ lb) {
   extern __shared__ __align__(16) unsigned char p_smem_raw[];
   PersistSmem& S = *reinterpret_cast<PersistSmem*>(p_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -205,7 +205,10 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
 
   // ---------------------------------------------------------------- iterations
   float4* W = work + (size_t)pair * wstride;
-  const float r = prm.search_r;
+  float* LB = lb + (size_t)pair * wstride;
+  const float r = prm.search_r;               // gate * 1.01
+  const float rmax = __fdividef(0.485f, inv_cs);  // largest ball that touches <= 2 cells per axis (~1.99 x gate)
+  const float slack = 0.5f * r;
   const int span = S.cmax[0] - ox, spany = S.cmax[1] - oy, spanz = S.cmax[2] - oz;
   int parity = 0;
   while (true) {
@@ -218,57 +221,86 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
     for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
     for (int i = crank * P_THREADS + tid; i < ns; i += CL * P_THREADS) {
       float4 p = W[i];
+      float lbv = LB[i];
       const bool fin = finite3(p.x, p.y, p.z);
       if (apply && fin) {
         const float3 q = xform_point(S.M, p.x, p.y, p.z);
+        // the bound decays by (an upper bound of) the distance this point just moved
+        lbv = lbv - (sqrtf(dist2_l2simple(q.x, q.y, q.z, p.x, p.y, p.z)) * 1.00001f + 1e-9f);
         p.x = q.x;
         p.y = q.y;
         p.z = q.z;
       }
-      // .w = (previous match slot + 1) << 16 | original source index
+      // .w = (cached match slot + 1) << 16 | original source index
       const unsigned wbits = __float_as_uint(p.w);
       const int orig = (int)(wbits & 0xFFFFu);
-      const int kp = (int)(wbits >> 16) - 1;
+      int kp = (int)(wbits >> 16) - 1;
       int best = -1, kbest = 0;
       float bd = INFINITY;
       if (fin) {
-        // Temporal coherence, still exact: the previous iteration's match bounds the NN distance from above, so only
-        // cells touched by the ball of THAT radius can hold a closer (or equal, lower-index) point.
-        float rr = r;
+        // Certified cache (exact): lbv is a lower bound of the true distance from this point to EVERY target point
+        // other than the cached one (to every target point if none is cached).  While the cached point is closer than
+        // that bound it is the strict nearest neighbour and no cell has to be visited; while the bound exceeds the gate
+        // an unmatched point stays unmatched.  Otherwise the ball that certainly contains the answer is rescanned
+        // (<= 2x2x2 cells) with some slack, which also renews the bound.
+        float s1 = 0.f;
+        bool scan;
+        float rr = rmax;
         if (kp >= 0) {
           bd = dist2_l2simple(p.x, p.y, p.z, S.tx[kp], S.ty[kp], S.tz[kp]);
-          best = (int)S.tidx[kp];
-          kbest = kp;
-          rr = fminf(r, __fmaf_rn(sqrtf(bd), 1.0001f, 1e-7f));
-        }
-        const int x0 = p_cell(p.x - rr, inv_cs) - ox, x1 = p_cell(p.x + rr, inv_cs) - ox;
-        const int y0 = p_cell(p.y - rr, inv_cs) - oy, y1 = p_cell(p.y + rr, inv_cs) - oy;
-        const int z0 = p_cell(p.z - rr, inv_cs) - oz, z1 = p_cell(p.z + rr, inv_cs) - oz;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0)) continue;
-          const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
-          if ((unsigned)ix > (unsigned)span || (unsigned)iy > (unsigned)spany || (unsigned)iz > (unsigned)spanz) continue;
-          const unsigned key = ((unsigned)ix << 20) | ((unsigned)iy << 10) | (unsigned)iz;
-          unsigned s = p_hash(key);
-          uint2 e = S.tab[s];
-          while (e.x != key && e.x != P_EMPTY) {
-            s = (s + 1) & (P_CAP - 1);
-            e = S.tab[s];
+          s1 = __fmaf_rn(sqrtf(bd), 1.0001f, 1e-7f);
+          scan = !(s1 < lbv);
+          if (s1 > rmax) {  // the cached point left the largest ball we can certify: start over
+            kp = -1;
+            bd = INFINITY;
+            scan = true;
+          } else {
+            best = (int)S.tidx[kp];
+            kbest = kp;
+            rr = fminf(rmax, s1 + slack);
           }
-          if (e.x != key) continue;
-          const int b = (int)(e.y >> 16), en = b + (int)(e.y & 0xFFFFu);
-          for (int k = b; k < en; ++k) {
-            const float d = dist2_l2simple(p.x, p.y, p.z, S.tx[k], S.ty[k], S.tz[k]);
-            const int idx = (int)S.tidx[k];
-            if (d < bd || (d == bd && idx < best)) {
-              bd = d;
-              best = idx;
-              kbest = k;
+        } else {
+          scan = !(lbv > r);
+        }
+        if (scan) {
+          float d2nd = INFINITY;  // smallest squared distance among scanned points other than the winner
+          const int x0 = p_cell(p.x - rr, inv_cs) - ox, x1 = p_cell(p.x + rr, inv_cs) - ox;
+          const int y0 = p_cell(p.y - rr, inv_cs) - oy, y1 = p_cell(p.y + rr, inv_cs) - oy;
+          const int z0 = p_cell(p.z - rr, inv_cs) - oz, z1 = p_cell(p.z + rr, inv_cs) - oz;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0)) continue;
+            const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
+            if ((unsigned)ix > (unsigned)span || (unsigned)iy > (unsigned)spany || (unsigned)iz > (unsigned)spanz) continue;
+            const unsigned key = ((unsigned)ix << 20) | ((unsigned)iy << 10) | (unsigned)iz;
+            unsigned s = p_hash(key);
+            uint2 e = S.tab[s];
+            while (e.x != key && e.x != P_EMPTY) {
+              s = (s + 1) & (P_CAP - 1);
+              e = S.tab[s];
+            }
+            if (e.x != key) continue;
+            const int b = (int)(e.y >> 16), en = b + (int)(e.y & 0xFFFFu);
+            for (int k = b; k < en; ++k) {
+              if (k == kp) continue;  // the cached point is already the incumbent
+              const float d = dist2_l2simple(p.x, p.y, p.z, S.tx[k], S.ty[k], S.tz[k]);
+              const int idx = (int)S.tidx[k];
+              if (d < bd || (d == bd && idx < best)) {
+                d2nd = bd;
+                bd = d;
+                best = idx;
+                kbest = k;
+              } else {
+                d2nd = fminf(d2nd, d);
+              }
             }
           }
+          // points outside the scanned cells are farther than rr minus the rounding of the cell-boundary test
+          const float edge = rr - 2e-7f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + rr);
+          lbv = fminf(sqrtf(d2nd), edge) * 0.99999f;
         }
       }
+      LB[i] = lbv;
       p.w = __uint_as_float(((unsigned)(best >= 0 ? kbest + 1 : 0) << 16) | (unsigned)orig);
       W[i] = p;
       const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
