@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-contexts", type=int, default=4)
     ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--e2e-lock", default="nosync", choices=["sync", "nosync", "none"],
+                    help="serialise transfers per direction (sync: hold the lock until the copy completed)")
+    ap.add_argument("--e2e-trace", action="store_true", help="print per-chunk phase timestamps of the timed e2e pipeline to stderr")
     return ap.parse_args()
 
 
@@ -335,22 +338,39 @@ def main():
                 # frames lo .. hi: pair i registers frame i+1 onto frame i
                 # one transfer per direction at a time: the contexts fall into a staggered pipeline (A computes while B
                 # uploads and C downloads) instead of moving in lockstep and sharing each PCIe direction
+                t0 = time.perf_counter()
                 with h2d_lock:
+                    t1 = time.perf_counter()
                     W_["frames"].upload_raw(in_rows[lo:hi + 1].ctypes.data_as(C.c_void_p), cnts, W, H, R.LAYOUT_PCL32)
-                    cw.sync()
+                    if a.e2e_lock == "sync":
+                        cw.sync()
+                t2 = time.perf_counter()
                 R.register_pairs(cw, W_["frames"], si, ti, coarse, icp=icp, ndt=ndt, guess=guess, out_transformed=W_["out"])
+                t3 = time.perf_counter()
                 with d2h_lock:
+                    t4 = time.perf_counter()
                     cw.check(L.rspcl_cloud_download(cw.h, W_["out"].h, out_rows[lo:hi].ctypes.data_as(C.c_void_p),
                                                     R.LAYOUT_PCL32, C.c_longlong(cp * NPX), W_["oc"].ctypes.data_as(C.c_void_p)))
+                t5 = time.perf_counter()
+                if timed and a.e2e_trace:
+                    trace.append((w, st_i, ci, t0, t1, t2, t3, t4, t5))
         if timed:
             cw.timer_mark()
 
-    h2d_lock, d2h_lock = threading.Lock(), threading.Lock()
+    import contextlib
+    h2d_lock, d2h_lock = (contextlib.nullcontext(), contextlib.nullcontext()) if a.e2e_lock == "none" else (threading.Lock(), threading.Lock())
+    trace = []
     pool = ThreadPoolExecutor(n_ctx)
     list(pool.map(lambda w: run_chunks(w, max(1, a.warmup - 1), False), range(n_ctx)))
     barrier()
     list(pool.map(lambda w: run_chunks(w, a.steps, True), range(n_ctx)))
     ms_e2e = max_over_ranks(R.timer_span([w["ctx"] for w in workers]))
+    if a.e2e_trace and trace:
+        tz = min(t[3] for t in trace)
+        for t in sorted(trace, key=lambda t: t[3]):
+            sys.stderr.write("ctx %d step %d chunk %d: wait_h2d %.2f upload %.2f compute %.2f wait_d2h %.2f download %.2f  [start %.2f end %.2f ms]\n" % (
+                t[0], t[1], t[2], 1e3 * (t[4] - t[3]), 1e3 * (t[5] - t[4]), 1e3 * (t[6] - t[5]), 1e3 * (t[7] - t[6]),
+                1e3 * (t[8] - t[7]), 1e3 * (t[3] - tz), 1e3 * (t[8] - tz)))
     barrier()
     e2e = world * n_pairs * a.steps / (ms_e2e / 1e3)
     # the pipelined path must reproduce the single-context result

@@ -194,9 +194,124 @@ __device__ bool polar_rotation(const double* A, double* R) {
   return true;
 }
 
+// 1/x to full fp64 accuracy from the fp32 reciprocal and two Newton steps (a handful of DFMAs instead of the ~40
+// dependent instructions of an IEEE fp64 division); x must be a normal number inside the float range.
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r = (double)__frcp_rn((float)x);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
+// Fast path of the same polar factor: the scaled Newton iteration runs in fp32 (4-cycle FMAs instead of the fp64
+// chain); its result is re-orthogonalised by one fp64 Newton step, and the rotation error k that is left is removed in
+// fp64 to second order: with M = Y^T A = Q H (Q = exp([k]x) the small rotation still missing, H symmetric positive
+// definite) the skew part of M satisfies (tr(H) I - H) k = 2 axial(skew M), a 3x3 SPD solve, and
+// R = Y (I + [k]x + [k]x^2 / 2).  One pass squares the error (|k| ~ 1e-6 -> 1e-12); a second pass runs when the first
+// correction was large (ill-conditioned covariances, e.g. a wall seen head-on).  Equals U V^T to ~1e-14.  Returns false
+// (caller falls back to the fp64 iteration / SVD) if anything looks degenerate.
+__device__ bool polar_rotation_fast(const double* A, double* R) {
+  double fro2 = 0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) fro2 = fma(A[i], A[i], fro2);
+  const float scale_f = sqrtf((float)fro2 * (1.0f / 3.0f));
+  if (!(scale_f > 1e-30f && scale_f < 1e30f)) return false;
+  const double det0 = det3(A), scale = (double)scale_f;
+  if (!(det0 > 1e-7 * scale * scale * scale)) return false;
+  const float inv_scale = __frcp_rn(scale_f);
+  float X[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) X[i] = (float)A[i] * inv_scale;
+  bool scaling = true, done = false;
+#pragma unroll 1
+  for (int it = 0; it < 20 && !done; ++it) {
+    const float c[9] = {X[4] * X[8] - X[5] * X[7], X[5] * X[6] - X[3] * X[8], X[3] * X[7] - X[4] * X[6],
+                        X[2] * X[7] - X[1] * X[8], X[0] * X[8] - X[2] * X[6], X[1] * X[6] - X[0] * X[7],
+                        X[1] * X[5] - X[2] * X[4], X[2] * X[3] - X[0] * X[5], X[0] * X[4] - X[1] * X[3]};
+    const float det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
+    if (!(det > 0.f)) return false;
+    const float idet = __fdividef(1.0f, det);
+    float a = 0.5f, bq = 0.5f * idet;
+    if (scaling) {
+      const float nx = (X[0] * X[0] + X[1] * X[1] + X[2] * X[2]) + (X[3] * X[3] + X[4] * X[4] + X[5] * X[5]) +
+                       (X[6] * X[6] + X[7] * X[7] + X[8] * X[8]);
+      const float ny = (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) + (c[3] * c[3] + c[4] * c[4] + c[5] * c[5]) +
+                       (c[6] * c[6] + c[7] * c[7] + c[8] * c[8]);
+      const float g2 = sqrtf(__fdividef(ny * idet * idet, nx));  // g^2
+      const float ig = rsqrtf(g2);
+      if (fabsf(g2 - 1.0f) < 2e-2f) scaling = false;
+      a = 0.5f * g2 * ig;  // g / 2
+      bq = 0.5f * idet * ig;
+    }
+    float diff = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float v = a * X[i] + bq * c[i];
+      diff += (v - X[i]) * (v - X[i]);
+      X[i] = v;
+    }
+    if (!scaling && diff <= 1e-10f) done = true;
+  }
+  if (!done) return false;
+  double Y[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Y[i] = (double)X[i];
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    {  // one fp64 Newton step: orthogonality error e -> e^2 / 2
+      const double c[9] = {Y[4] * Y[8] - Y[5] * Y[7], Y[5] * Y[6] - Y[3] * Y[8], Y[3] * Y[7] - Y[4] * Y[6],
+                           Y[2] * Y[7] - Y[1] * Y[8], Y[0] * Y[8] - Y[2] * Y[6], Y[1] * Y[6] - Y[0] * Y[7],
+                           Y[1] * Y[5] - Y[2] * Y[4], Y[2] * Y[3] - Y[0] * Y[5], Y[0] * Y[4] - Y[1] * Y[3]};
+      const double det = Y[0] * c[0] + Y[1] * c[1] + Y[2] * c[2];
+      if (!(det > 0.5 && det < 2.0)) return false;
+      const double h = 0.5 * rcp_fast(det);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Y[i] = fma(0.5, Y[i], h * c[i]);
+    }
+    // M = Y^T A, G = tr(H) I - H with H = sym(M), rhs = 2 axial(skew(M))
+    double M[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) M[r * 3 + c] = fma(Y[0 + r], A[0 + c], fma(Y[3 + r], A[3 + c], Y[6 + r] * A[6 + c]));
+    const double h01 = 0.5 * (M[1] + M[3]), h02 = 0.5 * (M[2] + M[6]), h12 = 0.5 * (M[5] + M[7]);
+    const double tr = M[0] + M[4] + M[8];
+    const double G[9] = {tr - M[0], -h01, -h02, -h01, tr - M[4], -h12, -h02, -h12, tr - M[8]};
+    const double b[3] = {M[7] - M[5], M[2] - M[6], M[3] - M[1]};
+    const double gc[6] = {G[4] * G[8] - G[5] * G[5], G[5] * G[2] - G[1] * G[8], G[1] * G[5] - G[4] * G[2],
+                          G[0] * G[8] - G[2] * G[2], G[1] * G[2] - G[0] * G[5], G[0] * G[4] - G[1] * G[1]};  // adj(G)
+    const double gdet = G[0] * gc[0] + G[1] * gc[1] + G[2] * gc[2];
+    const float gdet_f = (float)gdet;
+    if (!(gdet_f > 1e-30f && gdet_f < 1e30f)) return false;
+    const double ig = rcp_fast(gdet);
+    const double k0 = (gc[0] * b[0] + gc[1] * b[1] + gc[2] * b[2]) * ig;
+    const double k1 = (gc[1] * b[0] + gc[3] * b[1] + gc[4] * b[2]) * ig;
+    const double k2 = (gc[2] * b[0] + gc[4] * b[1] + gc[5] * b[2]) * ig;
+    const double kk = k0 * k0 + k1 * k1 + k2 * k2;
+    if (!(kk < 1e-4)) return false;  // the fp32 stage was nowhere near: the exact path decides
+    // Q = I + K + K^2 / 2, K = [k]x
+    const double Q[9] = {1.0 - 0.5 * (k1 * k1 + k2 * k2), -k2 + 0.5 * k0 * k1, k1 + 0.5 * k0 * k2,
+                         k2 + 0.5 * k0 * k1, 1.0 - 0.5 * (k0 * k0 + k2 * k2), -k0 + 0.5 * k1 * k2,
+                         -k1 + 0.5 * k0 * k2, k0 + 0.5 * k1 * k2, 1.0 - 0.5 * (k0 * k0 + k1 * k1)};
+    double Z[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Z[r * 3 + c] = fma(Y[r * 3 + 0], Q[0 + c], fma(Y[r * 3 + 1], Q[3 + c], Y[r * 3 + 2] * Q[6 + c]));
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Y[i] = Z[i];
+    if (kk < 1e-11) {  // |k| < 3e-6: what is left after this pass is O(k^2) (measured ~1e-14 at |k| = 2e-6)
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = Y[i];
+      return true;
+    }
+  }
+  return false;
+}
+
 // pcl::umeyama(src, dst, with_scaling=false) from raw fp64 moments: S = {n, sum s, sum t, sum s_r t_c}
 __device__ void umeyama_from_moments(const double* S, float* T) {
-  const double n = S[0], inv_n = 1.0 / n;
+  const double n = S[0], inv_n = rcp_fast(n);
   const double ms[3] = {S[1] * inv_n, S[2] * inv_n, S[3] * inv_n};
   const double mt[3] = {S[4] * inv_n, S[5] * inv_n, S[6] * inv_n};
   double sigma[9];  // sigma(r,c) = mean((t_r - mt_r)(s_c - ms_c))
@@ -205,7 +320,7 @@ __device__ void umeyama_from_moments(const double* S, float* T) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) sigma[r * 3 + c] = S[7 + c * 3 + r] * inv_n - mt[r] * ms[c];
   double R[9];
-  if (!polar_rotation(sigma, R)) {
+  if (!polar_rotation_fast(sigma, R) && !polar_rotation(sigma, R)) {
     double U[9], sv[3], V[9];
     svd3(sigma, U, sv, V);
     const double d = det3(U) * det3(V);
@@ -292,7 +407,7 @@ __device__ void icp_solve_pair(IcpState* S, const double* sums, const IcpDevPara
   S->apply_inc = 1;
   mat4_mul(T, S->final_T, S->final_T);
   const int it = ++S->iterations;
-  const double mse = sums[16] / (double)n_corr;
+  const double mse = sums[16] * rcp_fast((double)n_corr);  // within 1 ulp of the quotient
   S->mse = mse;
   // DefaultConvergenceCriteria::hasConverged
   int state = RSPCL_CONV_NOT_CONVERGED;
@@ -631,6 +746,12 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       CU(ctx, scratch_alloc(ctx, &d_order, (size_t)S));
       CU(ctx, small_h2d(ctx, d_order, order.data(), (size_t)S * sizeof(int)));
       const float inv_cs_p = 1.0f / (float)(prm->max_corr_dist * 4.1);
+      long long* d_dbg = nullptr;  // RSPCL_PERSIST_DBG=1: per-CTA phase cycle counters, printed to stderr
+      const bool want_dbg = getenv("RSPCL_PERSIST_DBG") != nullptr;
+      if (want_dbg) {
+        CU(ctx, scratch_alloc(ctx, &d_dbg, (size_t)S * 4 * 8));
+        CU(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)S * 4 * 8 * sizeof(long long), ctx->stream));
+      }
       static bool attr_set = false;
       if (!attr_set) {
         CU(ctx, cudaFuncSetAttribute(k_icp_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
@@ -657,11 +778,11 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       ProfScope prof(ctx, "k_icp_persist", 0.0);
       cudaError_t le;
       if (cl == 4)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_dbg);
       else if (cl == 2)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_dbg);
       else
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_dbg);
       CU(ctx, le);
       LAUNCH_CHECK(ctx);
       prof.end();
@@ -672,6 +793,19 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       CU(ctx, small_d2h(ctx, hst0.data(), st, (size_t)S * sizeof(IcpState)));
       CU(ctx, small_d2h(ctx, hc.data(), src->count, (size_t)S * sizeof(int)));
       CU(ctx, ctx_sync(ctx));
+      if (want_dbg) {
+        std::vector<long long> hd((size_t)S * cl * 8);
+        CU(ctx, cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "persist dbg: S=%d cl=%d  [pair crank ns iters | phaseA waitA phaseB reduce+exchange solve head | total] kcycles\n", S, cl);
+        for (int s = 0; s < S; ++s)
+          for (int c = 0; c < cl; ++c) {
+            const long long* D = &hd[((size_t)s * cl + c) * 8];
+            fprintf(stderr, "  %3d %d %6lld %3d | %7.1f %7.1f %7.1f %7.1f %7.1f %7.1f | %8.1f\n", s, c, D[6], hst0[s].iterations, D[0] / 1e3,
+                    D[1] / 1e3, D[2] / 1e3, D[3] / 1e3, D[4] / 1e3, D[5] / 1e3, D[7] / 1e3);
+          }
+        scratch_free(ctx, d_dbg);
+      }
       scratch_free(ctx, d_status);
       scratch_free(ctx, d_order);
       scratch_free(ctx, d_lb);

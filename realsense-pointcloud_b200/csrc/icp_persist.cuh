@@ -22,12 +22,36 @@ constexpr int P_NTMAX = 12288;                 // target points resident per CTA
 constexpr int P_CAP = 4096;                    // cell-table slots (power of two)
 constexpr unsigned P_EMPTY = 0xFFFFFFFFu;
 constexpr int P_WARPS = P_THREADS / 32;
+constexpr int P_WL = 7168;                     // work-list entries (points per phase-A/B round)
+
+// MUFU.SQRT (2^-22 relative error): only used for bounds that carry a 1e-5 safety margin
+__device__ __forceinline__ float sqrt_approx(float v) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+__device__ __forceinline__ void icp_accumulate(double* acc, float px, float py, float pz, float qx, float qy, float qz,
+                                               float d2) {
+  const double sx = px, sy = py, sz = pz, tx = qx, ty = qy, tz = qz;
+  acc[0] += 1.0;
+  acc[1] += sx; acc[2] += sy; acc[3] += sz;
+  acc[4] += tx; acc[5] += ty; acc[6] += tz;
+  acc[7] += sx * tx; acc[8] += sx * ty; acc[9] += sx * tz;
+  acc[10] += sy * tx; acc[11] += sy * ty; acc[12] += sy * tz;
+  acc[13] += sz * tx; acc[14] += sz * ty; acc[15] += sz * tz;
+  acc[16] += (double)d2;
+}
 
 struct PersistSmem {
   float tx[P_NTMAX], ty[P_NTMAX], tz[P_NTMAX];
   unsigned short tidx[P_NTMAX];
   uint2 tab[P_CAP];                 // {key, start << 16 | count}
-  unsigned short fill[P_CAP];       // build-time cursors
+  union {
+    unsigned short fill[P_CAP];     // build-time cursors
+    unsigned short wl[P_WL];        // per-iteration work list of points that need a cell scan (offset within the round)
+  };
+  int nwork;
   double red[P_WARPS][NRED];
   double part[2][NRED];             // this CTA's partial sums, double-buffered by iteration parity (read by the
                                     // other CTAs of the cluster through DSMEM)
@@ -49,7 +73,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstride, IcpState* __restrict__ st_g,
               const float4* __restrict__ tgt, const int* __restrict__ tcount, int tstride, int shared_target,
               IcpDevParams prm, float inv_cs, int* __restrict__ first_corr, int* __restrict__ status,
-              const int* __restrict__ order, float* __restrict__ lb) {
+              const int* __restrict__ order, float* __restrict__ lb, long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char p_smem_raw[];
   PersistSmem& S = *reinterpret_cast<PersistSmem*>(p_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -211,67 +235,115 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
   const float slack = 0.5f * r;
   const int span = S.cmax[0] - ox, spany = S.cmax[1] - oy, spanz = S.cmax[2] - oz;
   int parity = 0;
+  long long tph[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();  // debug phase timers (thread 0; only stored if dbg != nullptr)
+#define P_TICK(k) do { if (dbg && tid == 0) { const long long n_ = clock64(); tph[k] += n_ - tc; tc = n_; } } while (0)
+  if (dbg && tid == 0) dbg[((size_t)pair * CL + crank) * 8 + 6] = tc;
   while (true) {
     if (tid < 16) S.M[tid] = S.st.inc_T[tid];
     __syncthreads();
+    P_TICK(5);
     const int apply = S.st.apply_inc;
     const bool want_corr = first_corr != nullptr && S.st.iterations == 0;
     double acc[NRED];
 #pragma unroll
     for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
-    for (int i = crank * P_THREADS + tid; i < ns; i += CL * P_THREADS) {
-      float4 p = W[i];
-      float lbv = LB[i];
-      const bool fin = finite3(p.x, p.y, p.z);
-      if (apply && fin) {
-        const float3 q = xform_point(S.M, p.x, p.y, p.z);
-        // the bound decays by (an upper bound of) the distance this point just moved
-        lbv = lbv - (sqrtf(dist2_l2simple(q.x, q.y, q.z, p.x, p.y, p.z)) * 1.00001f + 1e-9f);
-        p.x = q.x;
-        p.y = q.y;
-        p.z = q.z;
+    // Certified cache (exact).  LB[i] is a lower bound of the true distance from source point i to EVERY target point
+    // other than its cached match (to every target point if none is cached).  While the cached match is closer than
+    // that bound it is the strict nearest neighbour; while the bound exceeds the gate an unmatched point stays
+    // unmatched: no cell is visited (phase A, straight-line code, two points in flight per thread).  The few points
+    // whose bound no longer decides go to a shared-memory work list and are rescanned load-balanced over the whole CTA
+    // (phase B, <= 2x2x2 cells), which also renews their bound.
+    const int share = (ns + CL - 1) / CL;           // this CTA's contiguous slice [lo, hi) of the (spatially sorted) source
+    const int lo = crank * share, hi = min(ns, lo + share);
+    for (int base = lo; base < hi; base += P_WL) {  // one round unless the slice exceeds the work list
+      const int end = min(hi, base + P_WL);
+      if (tid == 0) S.nwork = 0;
+      __syncthreads();
+      // ---------------- phase A (software-pipelined: the next point's loads are in flight while this one is processed)
+      {
+        int i = base + tid;
+        float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ln = 0.f;
+        if (i < end) {
+          pn = W[i];
+          ln = LB[i];
+        }
+        for (; i < end; i += P_THREADS) {
+          float4 p = pn;
+          float lbv = ln;
+          if (i + P_THREADS < end) {
+            pn = W[i + P_THREADS];
+            ln = LB[i + P_THREADS];
+          }
+          const bool fin = finite3(p.x, p.y, p.z);
+          if (apply && fin) {
+            const float3 q = xform_point(S.M, p.x, p.y, p.z);
+            // the bound decays by (an upper bound of) the distance this point just moved
+            lbv = lbv - __fmaf_rn(sqrt_approx(dist2_l2simple(q.x, q.y, q.z, p.x, p.y, p.z)), 1.00001f, 1e-9f);
+            p.x = q.x;
+            p.y = q.y;
+            p.z = q.z;
+            W[i] = p;
+          }
+          LB[i] = lbv;
+          if (!fin) {
+            if (want_corr) first_corr[(size_t)pair * wstride + (int)(__float_as_uint(p.w) & 0xFFFFu)] = -1;
+            continue;
+          }
+          // .w = (cached match slot + 1) << 16 | original source index
+          const unsigned wbits = __float_as_uint(p.w);
+          const int kp = (int)(wbits >> 16) - 1;
+          bool valid;
+          float bd = INFINITY;
+          if (kp >= 0) {
+            bd = dist2_l2simple(p.x, p.y, p.z, S.tx[kp], S.ty[kp], S.tz[kp]);
+            valid = __fmaf_rn(sqrt_approx(bd), 1.0001f, 1e-7f) < lbv;
+          } else {
+            valid = lbv > r;
+          }
+          if (!valid) {
+            S.wl[atomicAdd(&S.nwork, 1)] = (unsigned short)(i - base);
+            continue;
+          }
+          const bool ok = kp >= 0 && !((double)bd > prm.max_dist_sqr);
+          if (want_corr) first_corr[(size_t)pair * wstride + (int)(wbits & 0xFFFFu)] = ok ? (int)S.tidx[kp] : -1;
+          if (ok) icp_accumulate(acc, p.x, p.y, p.z, S.tx[kp], S.ty[kp], S.tz[kp], bd);
+        }
       }
-      // .w = (cached match slot + 1) << 16 | original source index
-      const unsigned wbits = __float_as_uint(p.w);
-      const int orig = (int)(wbits & 0xFFFFu);
-      int kp = (int)(wbits >> 16) - 1;
-      int best = -1, kbest = 0;
-      float bd = INFINITY;
-      if (fin) {
-        // Certified cache (exact): lbv is a lower bound of the true distance from this point to EVERY target point
-        // other than the cached one (to every target point if none is cached).  While the cached point is closer than
-        // that bound it is the strict nearest neighbour and no cell has to be visited; while the bound exceeds the gate
-        // an unmatched point stays unmatched.  Otherwise the ball that certainly contains the answer is rescanned
-        // (<= 2x2x2 cells) with some slack, which also renews the bound.
-        float s1 = 0.f;
-        bool scan;
-        float rr = rmax;
+      P_TICK(0);
+      __syncthreads();
+      P_TICK(1);
+      // ---------------- phase B: 8 lanes per work item, one neighbour cell each, merged with xor shuffles
+      const int nwork = S.nwork;
+      for (int jb = wid * 4; jb < nwork; jb += P_WARPS * 4) {  // warp-uniform trip count (full-mask shuffles below)
+        const int j = jb + (lane >> 3), c = lane & 7;
+        const bool active = j < nwork;
+        const int i = base + (active ? (int)S.wl[j] : 0);
+        const float4 p = W[i];  // already transformed by phase A
+        const unsigned wbits = __float_as_uint(p.w);
+        const int orig = (int)(wbits & 0xFFFFu);
+        int kp = (int)(wbits >> 16) - 1;
+        float bdc = INFINITY, rr = rmax;  // cached incumbent
         if (kp >= 0) {
-          bd = dist2_l2simple(p.x, p.y, p.z, S.tx[kp], S.ty[kp], S.tz[kp]);
-          s1 = __fmaf_rn(sqrtf(bd), 1.0001f, 1e-7f);
-          scan = !(s1 < lbv);
+          bdc = dist2_l2simple(p.x, p.y, p.z, S.tx[kp], S.ty[kp], S.tz[kp]);
+          const float s1 = __fmaf_rn(sqrt_approx(bdc), 1.0001f, 1e-7f);
           if (s1 > rmax) {  // the cached point left the largest ball we can certify: start over
             kp = -1;
-            bd = INFINITY;
-            scan = true;
+            bdc = INFINITY;
           } else {
-            best = (int)S.tidx[kp];
-            kbest = kp;
             rr = fminf(rmax, s1 + slack);
           }
-        } else {
-          scan = !(lbv > r);
         }
-        if (scan) {
-          float d2nd = INFINITY;  // smallest squared distance among scanned points other than the winner
+        int best = -1, kbest = 0;
+        float bd = INFINITY, d2nd = INFINITY;  // d2nd: smallest squared distance among scanned points other than the winner
+        {
           const int x0 = p_cell(p.x - rr, inv_cs) - ox, x1 = p_cell(p.x + rr, inv_cs) - ox;
           const int y0 = p_cell(p.y - rr, inv_cs) - oy, y1 = p_cell(p.y + rr, inv_cs) - oy;
           const int z0 = p_cell(p.z - rr, inv_cs) - oz, z1 = p_cell(p.z + rr, inv_cs) - oz;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0)) continue;
-            const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
-            if ((unsigned)ix > (unsigned)span || (unsigned)iy > (unsigned)spany || (unsigned)iz > (unsigned)spanz) continue;
+          const bool dup = ((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0);
+          const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
+          const bool inside = (unsigned)ix <= (unsigned)span && (unsigned)iy <= (unsigned)spany && (unsigned)iz <= (unsigned)spanz;
+          if (active && !dup && inside) {
             const unsigned key = ((unsigned)ix << 20) | ((unsigned)iy << 10) | (unsigned)iz;
             unsigned s = p_hash(key);
             uint2 e = S.tab[s];
@@ -279,43 +351,61 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
               s = (s + 1) & (P_CAP - 1);
               e = S.tab[s];
             }
-            if (e.x != key) continue;
-            const int b = (int)(e.y >> 16), en = b + (int)(e.y & 0xFFFFu);
-            for (int k = b; k < en; ++k) {
-              if (k == kp) continue;  // the cached point is already the incumbent
-              const float d = dist2_l2simple(p.x, p.y, p.z, S.tx[k], S.ty[k], S.tz[k]);
-              const int idx = (int)S.tidx[k];
-              if (d < bd || (d == bd && idx < best)) {
-                d2nd = bd;
-                bd = d;
-                best = idx;
-                kbest = k;
-              } else {
-                d2nd = fminf(d2nd, d);
+            if (e.x == key) {
+              const int b = (int)(e.y >> 16), en = b + (int)(e.y & 0xFFFFu);
+#pragma unroll 4
+              for (int k = b; k < en; ++k) {
+                const float d = (k == kp) ? INFINITY : dist2_l2simple(p.x, p.y, p.z, S.tx[k], S.ty[k], S.tz[k]);
+                const int idx = (int)S.tidx[k];
+                if (d < bd || (d == bd && idx < best)) {
+                  d2nd = bd;
+                  bd = d;
+                  best = idx;
+                  kbest = k;
+                } else {
+                  d2nd = fminf(d2nd, d);
+                }
               }
             }
           }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {  // top-2 merge across the 8 cells (every lane ends with the group result)
+          const float obd = __shfl_xor_sync(0xffffffffu, bd, o), o2 = __shfl_xor_sync(0xffffffffu, d2nd, o);
+          const int ob = __shfl_xor_sync(0xffffffffu, best, o), ok_ = __shfl_xor_sync(0xffffffffu, kbest, o);
+          if (obd < bd || (obd == bd && ob < best)) {
+            d2nd = fminf(o2, bd);
+            bd = obd;
+            best = ob;
+            kbest = ok_;
+          } else {
+            d2nd = fminf(d2nd, obd);
+          }
+        }
+        if (kp >= 0) {  // merge the cached incumbent (skipped by the scan)
+          const int bc = (int)S.tidx[kp];
+          if (bdc < bd || (bdc == bd && bc < best)) {
+            d2nd = bd;
+            bd = bdc;
+            best = bc;
+            kbest = kp;
+          } else {
+            d2nd = fminf(d2nd, bdc);
+          }
+        }
+        if (active && c == 0) {
           // points outside the scanned cells are farther than rr minus the rounding of the cell-boundary test
           const float edge = rr - 2e-7f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + rr);
-          lbv = fminf(sqrtf(d2nd), edge) * 0.99999f;
+          LB[i] = fminf(sqrt_approx(d2nd), edge) * 0.9999f;
+          W[i].w = __uint_as_float(((unsigned)(best >= 0 ? kbest + 1 : 0) << 16) | (unsigned)orig);
+          const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
+          if (want_corr) first_corr[(size_t)pair * wstride + orig] = ok ? best : -1;
+          if (ok) icp_accumulate(acc, p.x, p.y, p.z, S.tx[kbest], S.ty[kbest], S.tz[kbest], bd);
         }
       }
-      LB[i] = lbv;
-      p.w = __uint_as_float(((unsigned)(best >= 0 ? kbest + 1 : 0) << 16) | (unsigned)orig);
-      W[i] = p;
-      const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
-      if (want_corr) first_corr[(size_t)pair * wstride + orig] = ok ? best : -1;
-      if (ok) {
-        const double sx = p.x, sy = p.y, sz = p.z, tx = S.tx[kbest], ty = S.ty[kbest], tz = S.tz[kbest];
-        acc[0] += 1.0;
-        acc[1] += sx; acc[2] += sy; acc[3] += sz;
-        acc[4] += tx; acc[5] += ty; acc[6] += tz;
-        acc[7] += sx * tx; acc[8] += sx * ty; acc[9] += sx * tz;
-        acc[10] += sy * tx; acc[11] += sy * ty; acc[12] += sy * tz;
-        acc[13] += sz * tx; acc[14] += sz * ty; acc[15] += sz * tz;
-        acc[16] += (double)bd;
-      }
+      if (base + P_WL < hi) __syncthreads();  // the work list is reused by the next round
     }
+    P_TICK(2);
 #pragma unroll
     for (int k = 0; k < NRED; ++k) {
       const double v = warp_sum(acc[k]);
@@ -346,10 +436,19 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
       if (tid < NRED) S.tot[tid] = S.part[buf][tid];
       __syncthreads();
     }
+    P_TICK(3);
     if (tid == 0) icp_solve_pair(&S.st, S.tot, prm, &S.flags[1]);
+    P_TICK(4);
     __syncthreads();
     if (S.st.done) break;
   }
   if (CL > 1) cg::this_cluster().sync();  // no CTA leaves while a sibling may still read its partials
   if (tid == 0 && crank == 0) st_g[pair] = S.st;
+  if (dbg && tid == 0) {
+    long long* D = dbg + ((size_t)pair * CL + crank) * 8;
+    for (int k = 0; k < 6; ++k) D[k] = tph[k];
+    D[7] = clock64() - D[6];
+    D[6] = ns;
+  }
+#undef P_TICK
 }
