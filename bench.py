@@ -388,10 +388,10 @@ def main():
     step()
     ms_prof = ctx.timer_stop()
     ctx.profile(False)
-    kern = {k: ctx.profile_get(k) for k in ("k_icp_persist", "k_icp_step", "k_icp_solve", "grid_build", "k_canny_nms",
+    kern = {k: ctx.profile_get(k) for k in ("k_icp_persist", "k_icp_step", "k_icp_stream", "k_icp_rescan", "k_icp_solve", "grid_build", "k_canny_nms",
                                             "edge_hysteresis_compact", "k_approx_voxel", "k_transform2", "k_ndt_eval",
                                             "ndt_voxel_build")}
-    dom = "k_icp_persist" if kern["k_icp_persist"]["launches"] else "k_icp_step"
+    dom = "k_icp_persist" if kern["k_icp_persist"]["launches"] else ("k_icp_stream" if kern["k_icp_stream"]["launches"] else "k_icp_step")
     ki = kern[dom]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

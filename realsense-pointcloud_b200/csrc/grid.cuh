@@ -134,6 +134,113 @@ __device__ __forceinline__ int grid_nn_bounded(const DevGrid& g, int seg, float 
   return best;
 }
 
+// Same scan, additionally returning the position of the winner inside g.sorted and the smallest squared distance among
+// the OTHER scanned points (d2nd), skipping position `skip` (the caller's cached incumbent, merged by the caller).
+// Used by the certified-cache ICP passes (icp.cu): min(sqrt(d2nd), r) bounds the distance to every non-winner.
+__device__ __forceinline__ int grid_nn_top2(const DevGrid& g, int seg, float qx, float qy, float qz, float r, int skip,
+                                            float* out_d2, float* out_d2nd, int* out_pos, float4* out_pt) {
+  const int x0 = grid_cell(qx - r, g.inv_cs), x1 = grid_cell(qx + r, g.inv_cs);
+  const int y0 = grid_cell(qy - r, g.inv_cs), y1 = grid_cell(qy + r, g.inv_cs);
+  const int z0 = grid_cell(qz - r, g.inv_cs), z1 = grid_cell(qz + r, g.inv_cs);
+  int best = -1, bpos = -1;
+  float bd = INFINITY, d2nd = INFINITY;
+  float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (grid_in_range(x0, y0, z0) && grid_in_range(x1, y1, z1)) {
+    const int tseg = g.shared_target ? 0 : seg;
+    GridSlot sl[8];
+    unsigned long long keys[8];
+    unsigned hs[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const bool dup = ((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0);
+      const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
+      keys[c] = dup ? GRID_EMPTY : grid_key(tseg, ix, iy, iz);
+      hs[c] = grid_hash4(tseg, ix, iy, iz) & g.cap_mask;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sl[c] = grid_load_slot(&g.slots[hs[c]]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (keys[c] == GRID_EMPTY) continue;
+      GridSlot s = sl[c];
+      if (s.key != keys[c]) {
+        if (s.key == GRID_EMPTY) continue;
+        s = grid_probe_slow(g, keys[c], hs[c]);
+        if (s.cnt == 0) continue;
+      }
+      const int e = s.start + s.cnt;
+      for (int k = s.start; k < e; ++k) {
+        if (k == skip) continue;
+        const float4 t = __ldg(&g.sorted[k]);
+        const float d = dist2_l2simple(qx, qy, qz, t.x, t.y, t.z);
+        const int idx = __float_as_int(t.w);
+        if (d < bd || (d == bd && idx < best)) {
+          d2nd = bd;
+          bd = d;
+          best = idx;
+          bpos = k;
+          bp = t;
+        } else {
+          d2nd = fminf(d2nd, d);
+        }
+      }
+    }
+  }
+  *out_d2 = bd;
+  *out_d2nd = d2nd;
+  *out_pos = bpos;
+  *out_pt = bp;
+  return best;
+}
+
+// Wider certificate for a query with nothing inside its gate ball: scan the 3x3x3 cells around the query's own cell.
+// Every target point outside that block is at least one cell size away, so min(nearest found, cell size) bounds the
+// distance to every target point and the query does not have to be looked at again until it has moved that far.
+// Returns the nearest point found (position in g.sorted, -1 if none) and its squared distance / the runner-up's.
+static __device__ __noinline__ int grid_scan27_top2(const DevGrid& g, int seg, float qx, float qy, float qz, float* out_d2,
+                                             float* out_d2nd, float4* out_pt) {
+  const int cx = grid_cell(qx, g.inv_cs), cy = grid_cell(qy, g.inv_cs), cz = grid_cell(qz, g.inv_cs);
+  int bpos = -1, best = -1;
+  float bd = INFINITY, d2nd = INFINITY;
+  float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (grid_in_range(cx - 1, cy - 1, cz - 1) && grid_in_range(cx + 1, cy + 1, cz + 1)) {
+    const int tseg = g.shared_target ? 0 : seg;
+#pragma unroll 1
+    for (int c = 0; c < 27; ++c) {
+      const int ix = cx + (c % 3) - 1, iy = cy + ((c / 3) % 3) - 1, iz = cz + (c / 9) - 1;
+      const unsigned long long key = grid_key(tseg, ix, iy, iz);
+      unsigned h = grid_hash4(tseg, ix, iy, iz) & g.cap_mask;
+      GridSlot s = grid_load_slot(&g.slots[h]);
+      if (s.key != key) {
+        if (s.key == GRID_EMPTY) continue;
+        s = grid_probe_slow(g, key, h);
+        if (s.cnt == 0) continue;
+      }
+      const int e = s.start + s.cnt;
+      for (int k = s.start; k < e; ++k) {
+        const float4 t = __ldg(&g.sorted[k]);
+        const float d = dist2_l2simple(qx, qy, qz, t.x, t.y, t.z);
+        const int idx = __float_as_int(t.w);
+        if (d < bd || (d == bd && idx < best)) {
+          d2nd = bd;
+          bd = d;
+          best = idx;
+          bpos = k;
+          bp = t;
+        } else {
+          d2nd = fminf(d2nd, d);
+        }
+      }
+    }
+  } else {
+    bd = -1.f;  // out of the key range: no certificate
+  }
+  *out_d2 = bd;
+  *out_d2nd = d2nd;
+  *out_pt = bp;
+  return bpos;
+}
+
 // host API (grid.cu)
 int grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, float cell_size, DevGrid* g, int* d_range_flag);
 void grid_free(rspcl_ctx* ctx, DevGrid* g);

@@ -203,13 +203,16 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return r;
 }
 
-// Fast path of the same polar factor: the scaled Newton iteration runs in fp32 (4-cycle FMAs instead of the fp64
-// chain); its result is re-orthogonalised by one fp64 Newton step, and the rotation error k that is left is removed in
-// fp64 to second order: with M = Y^T A = Q H (Q = exp([k]x) the small rotation still missing, H symmetric positive
-// definite) the skew part of M satisfies (tr(H) I - H) k = 2 axial(skew M), a 3x3 SPD solve, and
-// R = Y (I + [k]x + [k]x^2 / 2).  One pass squares the error (|k| ~ 1e-6 -> 1e-12); a second pass runs when the first
-// correction was large (ill-conditioned covariances, e.g. a wall seen head-on).  Equals U V^T to ~1e-14.  Returns false
-// (caller falls back to the fp64 iteration / SVD) if anything looks degenerate.
+// Fast path of the same polar factor.  With an orthogonal seed Y near the answer, M = Y^T A = Q H (Q = exp([k]x) the
+// small rotation still missing, H symmetric positive definite) and the skew part of M satisfies
+// (tr(H) I - H) k = 2 axial(skew M), a 3x3 SPD solve in fp64; R = Y (I + [k]x + [k]x^2 / 2) squares the error
+// (|k| ~ 1e-6 -> ~1e-14 measured).  Seeds, cheapest first:
+//   pass 0: Y = I -- an ICP increment is a tiny rotation after the first iterations, so one pass usually finishes;
+//   else:   the scaled Newton iteration in fp32 (4-cycle FMAs instead of the fp64 chain), re-orthogonalised by one
+//           fp64 Newton step per pass.
+// The straight-line fp64 code is kept short on purpose: one thread runs it once per ICP iteration, so its cost is the
+// instruction fetch, not the arithmetic.  Returns false (caller falls back to the fp64 iteration / SVD) if anything
+// looks degenerate.
 __device__ bool polar_rotation_fast(const double* A, double* R) {
   double fro2 = 0;
 #pragma unroll
@@ -217,48 +220,15 @@ __device__ bool polar_rotation_fast(const double* A, double* R) {
   const float scale_f = sqrtf((float)fro2 * (1.0f / 3.0f));
   if (!(scale_f > 1e-30f && scale_f < 1e30f)) return false;
   const double det0 = det3(A), scale = (double)scale_f;
-  if (!(det0 > 1e-7 * scale * scale * scale)) return false;
-  const float inv_scale = __frcp_rn(scale_f);
-  float X[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) X[i] = (float)A[i] * inv_scale;
-  bool scaling = true, done = false;
+  // The correction passes only need tr(H) I - H positive definite (sigma_2 > |sigma_3|), i.e. they also cover the
+  // near-planar / reflected covariances for which Umeyama flips the last singular direction (the stationary point
+  // with that G positive definite IS the rotation maximising tr(R^T A)); only the fp32 Newton seed needs det(A) > 0.
+  const bool newton_ok = det0 > 1e-7 * scale * scale * scale;
+  double Y[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+  bool seeded = false;
 #pragma unroll 1
-  for (int it = 0; it < 20 && !done; ++it) {
-    const float c[9] = {X[4] * X[8] - X[5] * X[7], X[5] * X[6] - X[3] * X[8], X[3] * X[7] - X[4] * X[6],
-                        X[2] * X[7] - X[1] * X[8], X[0] * X[8] - X[2] * X[6], X[1] * X[6] - X[0] * X[7],
-                        X[1] * X[5] - X[2] * X[4], X[2] * X[3] - X[0] * X[5], X[0] * X[4] - X[1] * X[3]};
-    const float det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
-    if (!(det > 0.f)) return false;
-    const float idet = __fdividef(1.0f, det);
-    float a = 0.5f, bq = 0.5f * idet;
-    if (scaling) {
-      const float nx = (X[0] * X[0] + X[1] * X[1] + X[2] * X[2]) + (X[3] * X[3] + X[4] * X[4] + X[5] * X[5]) +
-                       (X[6] * X[6] + X[7] * X[7] + X[8] * X[8]);
-      const float ny = (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) + (c[3] * c[3] + c[4] * c[4] + c[5] * c[5]) +
-                       (c[6] * c[6] + c[7] * c[7] + c[8] * c[8]);
-      const float g2 = sqrtf(__fdividef(ny * idet * idet, nx));  // g^2
-      const float ig = rsqrtf(g2);
-      if (fabsf(g2 - 1.0f) < 2e-2f) scaling = false;
-      a = 0.5f * g2 * ig;  // g / 2
-      bq = 0.5f * idet * ig;
-    }
-    float diff = 0.f;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const float v = a * X[i] + bq * c[i];
-      diff += (v - X[i]) * (v - X[i]);
-      X[i] = v;
-    }
-    if (!scaling && diff <= 1e-10f) done = true;
-  }
-  if (!done) return false;
-  double Y[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) Y[i] = (double)X[i];
-#pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
-    {  // one fp64 Newton step: orthogonality error e -> e^2 / 2
+  for (int pass = 0; pass < 7; ++pass) {
+    if (pass > 0) {  // one fp64 Newton step: orthogonality error e -> e^2 / 2
       const double c[9] = {Y[4] * Y[8] - Y[5] * Y[7], Y[5] * Y[6] - Y[3] * Y[8], Y[3] * Y[7] - Y[4] * Y[6],
                            Y[2] * Y[7] - Y[1] * Y[8], Y[0] * Y[8] - Y[2] * Y[6], Y[1] * Y[6] - Y[0] * Y[7],
                            Y[1] * Y[5] - Y[2] * Y[4], Y[2] * Y[3] - Y[0] * Y[5], Y[0] * Y[4] - Y[1] * Y[3]};
@@ -282,14 +252,61 @@ __device__ bool polar_rotation_fast(const double* A, double* R) {
                           G[0] * G[8] - G[2] * G[2], G[1] * G[2] - G[0] * G[5], G[0] * G[4] - G[1] * G[1]};  // adj(G)
     const double gdet = G[0] * gc[0] + G[1] * gc[1] + G[2] * gc[2];
     const float gdet_f = (float)gdet;
-    if (!(gdet_f > 1e-30f && gdet_f < 1e30f)) return false;
-    const double ig = rcp_fast(gdet);
-    const double k0 = (gc[0] * b[0] + gc[1] * b[1] + gc[2] * b[2]) * ig;
-    const double k1 = (gc[1] * b[0] + gc[3] * b[1] + gc[4] * b[2]) * ig;
-    const double k2 = (gc[2] * b[0] + gc[4] * b[1] + gc[5] * b[2]) * ig;
-    const double kk = k0 * k0 + k1 * k1 + k2 * k2;
-    if (!(kk < 1e-4)) return false;  // the fp32 stage was nowhere near: the exact path decides
-    // Q = I + K + K^2 / 2, K = [k]x
+    // G positive definite (Sylvester) <=> H positive definite given det(A) > 0: the seed is within 90 degrees
+    bool good = G[0] > 0.0 && gc[5] > 0.0 && gdet_f > 1e-30f && gdet_f < 1e30f;
+    double k0 = 0, k1 = 0, k2 = 0, kk = 1.0;
+    if (good) {
+      const double ig = rcp_fast(gdet);
+      k0 = (gc[0] * b[0] + gc[1] * b[1] + gc[2] * b[2]) * ig;
+      k1 = (gc[1] * b[0] + gc[3] * b[1] + gc[4] * b[2]) * ig;
+      k2 = (gc[2] * b[0] + gc[4] * b[1] + gc[5] * b[2]) * ig;
+      kk = k0 * k0 + k1 * k1 + k2 * k2;
+      good = kk < 1e-2;  // |k| < 0.1 rad: inside the quadratic-convergence basin
+    }
+    if (!good) {
+      if (seeded || !newton_ok) return false;  // no usable seed: the exact path decides
+      // ---- fp32 scaled Newton seed (X <- (g X + X^-T / g) / 2)
+      seeded = true;
+      const float inv_scale = __frcp_rn(scale_f);
+      float X[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) X[i] = (float)A[i] * inv_scale;
+      bool scaling = true, done = false;
+#pragma unroll 1
+      for (int it = 0; it < 20 && !done; ++it) {
+        const float c[9] = {X[4] * X[8] - X[5] * X[7], X[5] * X[6] - X[3] * X[8], X[3] * X[7] - X[4] * X[6],
+                            X[2] * X[7] - X[1] * X[8], X[0] * X[8] - X[2] * X[6], X[1] * X[6] - X[0] * X[7],
+                            X[1] * X[5] - X[2] * X[4], X[2] * X[3] - X[0] * X[5], X[0] * X[4] - X[1] * X[3]};
+        const float det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
+        if (!(det > 0.f)) return false;
+        const float idet = __fdividef(1.0f, det);
+        float a = 0.5f, bq = 0.5f * idet;
+        if (scaling) {
+          const float nx = (X[0] * X[0] + X[1] * X[1] + X[2] * X[2]) + (X[3] * X[3] + X[4] * X[4] + X[5] * X[5]) +
+                           (X[6] * X[6] + X[7] * X[7] + X[8] * X[8]);
+          const float ny = (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) + (c[3] * c[3] + c[4] * c[4] + c[5] * c[5]) +
+                           (c[6] * c[6] + c[7] * c[7] + c[8] * c[8]);
+          const float g2 = sqrtf(__fdividef(ny * idet * idet, nx));  // g^2
+          const float ig = rsqrtf(g2);
+          if (fabsf(g2 - 1.0f) < 2e-2f) scaling = false;
+          a = 0.5f * g2 * ig;  // g / 2
+          bq = 0.5f * idet * ig;
+        }
+        float diff = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const float v = a * X[i] + bq * c[i];
+          diff += (v - X[i]) * (v - X[i]);
+          X[i] = v;
+        }
+        if (!scaling && diff <= 1e-10f) done = true;
+      }
+      if (!done) return false;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Y[i] = (double)X[i];
+      continue;
+    }
+    // Y <- Y Q, Q = I + K + K^2 / 2, K = [k]x
     const double Q[9] = {1.0 - 0.5 * (k1 * k1 + k2 * k2), -k2 + 0.5 * k0 * k1, k1 + 0.5 * k0 * k2,
                          k2 + 0.5 * k0 * k1, 1.0 - 0.5 * (k0 * k0 + k2 * k2), -k0 + 0.5 * k1 * k2,
                          -k1 + 0.5 * k0 * k2, k0 + 0.5 * k1 * k2, 1.0 - 0.5 * (k0 * k0 + k1 * k1)};
@@ -344,23 +361,6 @@ __device__ void umeyama_from_moments(const double* S, float* T) {
   }
 }
 
-// C = A * B (column-major float), entries ((a0 b0 + a1 b1) + a2 b2) + a3 b3 un-fused, as the oracle
-__device__ void mat4_mul(const float* A, const float* B, float* C) {
-  float R[16];
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float s = fmul(A[0 * 4 + r], B[c * 4 + 0]);
-      s = fadd(s, fmul(A[1 * 4 + r], B[c * 4 + 1]));
-      s = fadd(s, fmul(A[2 * 4 + r], B[c * 4 + 2]));
-      s = fadd(s, fmul(A[3 * 4 + r], B[c * 4 + 3]));
-      R[c * 4 + r] = s;
-    }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) C[i] = R[i];
-}
-
 __global__ void k_icp_init(IcpState* __restrict__ st, const float* __restrict__ guess, const double* __restrict__ prev_mse,
                            int n_seg) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -387,59 +387,82 @@ __global__ void k_icp_init(IcpState* __restrict__ st, const float* __restrict__ 
   st[s] = S;
 }
 
-// Umeyama + DefaultConvergenceCriteria for one pair (one thread), given the 17 combined sums
-__device__ void icp_solve_pair(IcpState* S, const double* sums, const IcpDevParams& prm, int* n_active) {
-  S->apply_inc = 0;
-  const int n_corr = (int)(sums[0] + 0.5);
-  S->n_corr = n_corr;
-  if (n_corr < prm.min_corr) {
-    // icp.hpp: "Not enough correspondences found" -> NO_CORRESPONDENCES, converged_ = false, loop exits
-    S->state = RSPCL_CONV_NO_CORRESPONDENCES;
-    S->converged = 0;
-    S->done = 1;
-    atomicSub(n_active, 1);
-    return;
-  }
-  float T[16];
-  umeyama_from_moments(sums, T);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) S->inc_T[i] = T[i];
-  S->apply_inc = 1;
-  mat4_mul(T, S->final_T, S->final_T);
-  const int it = ++S->iterations;
-  const double mse = sums[16] * rcp_fast((double)n_corr);  // within 1 ulp of the quotient
-  S->mse = mse;
-  // DefaultConvergenceCriteria::hasConverged
-  int state = RSPCL_CONV_NOT_CONVERGED;
-  bool conv = false;
-  if (it >= prm.max_iterations) {
-    state = RSPCL_CONV_ITERATIONS;
-    conv = true;
-  } else {
-    const double cos_angle = 0.5 * (double)(fadd(fadd(fadd(T[0], T[5]), T[10]), -1.0f));
-    const double tr2 = (double)fadd(fadd(fmul(T[12], T[12]), fmul(T[13], T[13])), fmul(T[14], T[14]));
-    if (cos_angle >= prm.rot_thr && tr2 <= prm.trans_thr) {
-      state = RSPCL_CONV_TRANSFORM;
-      conv = true;
+// Umeyama + DefaultConvergenceCriteria for one pair, given the 17 combined sums.  Called by one whole warp: lane 0 runs
+// the serial part, lanes 0-15 each produce one element of final = T * final.
+__device__ void icp_solve_pair(IcpState* S, const double* sums, const IcpDevParams& prm, int* n_active, int lane) {
+  if (lane == 0) {
+    S->apply_inc = 0;
+    const int n_corr = (int)(sums[0] + 0.5);
+    S->n_corr = n_corr;
+    if (n_corr < prm.min_corr) {
+      // icp.hpp: "Not enough correspondences found" -> NO_CORRESPONDENCES, converged_ = false, loop exits
+      S->state = RSPCL_CONV_NO_CORRESPONDENCES;
+      S->converged = 0;
+      S->done = 1;
+      atomicSub(n_active, 1);
     } else {
-      const double prev = S->prev_mse;
-      if (fabs(mse - prev) < prm.mse_abs) {
-        state = RSPCL_CONV_ABS_MSE;
-        conv = true;
-      } else if (fabs(mse - prev) / prev < prm.mse_rel) {
-        state = RSPCL_CONV_REL_MSE;
-        conv = true;
-      } else {
-        S->prev_mse = mse;
-      }
+      float T[16];
+      umeyama_from_moments(sums, T);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) S->inc_T[i] = T[i];
+      S->apply_inc = 1;
     }
   }
-  S->state = state;
-  if (conv) {
-    S->converged = 1;
-    S->done = 1;
-    atomicSub(n_active, 1);
+  __syncwarp();
+  if (!S->apply_inc) return;  // warp-uniform (read after the barrier)
+  {  // final = T * final (column-major), entries ((a0 b0 + a1 b1) + a2 b2) + a3 b3 un-fused, as the oracle
+    float v = 0.f;
+    if (lane < 16) {
+      const int r = lane & 3, c = lane >> 2;
+      const float* A = S->inc_T;
+      const float* B = S->final_T;
+      v = fmul(A[0 * 4 + r], B[c * 4 + 0]);
+      v = fadd(v, fmul(A[1 * 4 + r], B[c * 4 + 1]));
+      v = fadd(v, fmul(A[2 * 4 + r], B[c * 4 + 2]));
+      v = fadd(v, fmul(A[3 * 4 + r], B[c * 4 + 3]));
+    }
+    __syncwarp();
+    if (lane < 16) S->final_T[lane] = v;
   }
+  if (lane == 0) {
+    const float* T = S->inc_T;
+    const int n_corr = S->n_corr;
+    const int it = ++S->iterations;
+    const double mse = sums[16] * rcp_fast((double)n_corr);  // within 1 ulp of the quotient
+    S->mse = mse;
+    // DefaultConvergenceCriteria::hasConverged
+    int state = RSPCL_CONV_NOT_CONVERGED;
+    bool conv = false;
+    if (it >= prm.max_iterations) {
+      state = RSPCL_CONV_ITERATIONS;
+      conv = true;
+    } else {
+      const double cos_angle = 0.5 * (double)(fadd(fadd(fadd(T[0], T[5]), T[10]), -1.0f));
+      const double tr2 = (double)fadd(fadd(fmul(T[12], T[12]), fmul(T[13], T[13])), fmul(T[14], T[14]));
+      if (cos_angle >= prm.rot_thr && tr2 <= prm.trans_thr) {
+        state = RSPCL_CONV_TRANSFORM;
+        conv = true;
+      } else {
+        const double prev = S->prev_mse;
+        if (fabs(mse - prev) < prm.mse_abs) {
+          state = RSPCL_CONV_ABS_MSE;
+          conv = true;
+        } else if (fabs(mse - prev) / prev < prm.mse_rel) {
+          state = RSPCL_CONV_REL_MSE;
+          conv = true;
+        } else {
+          S->prev_mse = mse;
+        }
+      }
+    }
+    S->state = state;
+    if (conv) {
+      S->converged = 1;
+      S->done = 1;
+      atomicSub(n_active, 1);
+    }
+  }
+  __syncwarp();
 }
 
 template <bool BRUTE>
@@ -556,7 +579,7 @@ __global__ void __launch_bounds__(32) k_icp_solve(IcpState* __restrict__ st, con
     sums[lane] = v;
   }
   __syncwarp();
-  if (lane == 0) icp_solve_pair(&st[seg], sums, prm, n_active);
+  icp_solve_pair(&st[seg], sums, prm, n_active, lane);
 }
 
 __global__ void k_copy_work(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
@@ -620,6 +643,275 @@ __global__ void k_pack_i32(const int* __restrict__ v, const int* __restrict__ co
 
 #include "icp_persist.cuh"
 
+// ------------------------------------------------------------------------------------------------------------------
+// Certified-cache correspondence passes for clouds that do not fit the shared-memory kernel (global-memory grid).
+// Per source point: ci = position of its cached match inside g.sorted (-1: none), lb = lower bound of the true distance
+// to every OTHER target point (to every target point if ci < 0).  See icp_persist.cuh for why this is exact.
+//   k_icp_stream  one streaming pass over the working cloud: move the point, decay its bound by the distance moved,
+//                 re-measure the cached match (one 16 B gather, spatially coherent because source and g.sorted are both
+//                 in cell order) and, if the bound still decides, accumulate the 17 sums.  Points whose bound no longer
+//                 decides are appended to the block's slice of a work list IN POINT ORDER (ballot + prefix counts), so
+//                 every later sum is taken in a fixed order and results stay reproducible run to run.
+//                 Bytes per point: 16 R + 4 R (lb) + 4 R (ci) + 16 R (match) + 16 W + 4 W = 60 (algorithmic: 32).
+//   k_icp_rescan  re-queries the listed points in the voxel-hash grid (exact NN inside the gate ball, second-best
+//                 distance for the new bound) and adds its own partial sums.  The block slices are concatenated through
+//                 an exclusive scan of their counts (k_wl_offsets), item t always goes to the same thread.
+// Exact re-query of one source point: nearest target point inside the gate ball (grid scan) merged with the cached
+// incumbent `c`, the new cache position and the new certified bound.  Returns the winner's original index or -1.
+__device__ __forceinline__ int icp_requery(const DevGrid& g, int seg, const float4& p, int c, float r, float* out_bd,
+                                           int* out_pos, float4* out_t, float* out_lb) {
+  float bdc = INFINITY;
+  float4 tc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c >= 0) {
+    tc = __ldg(&g.sorted[c]);
+    bdc = dist2_l2simple(p.x, p.y, p.z, tc.x, tc.y, tc.z);
+  }
+  float bd, d2nd;
+  int pos;
+  float4 t;
+  int best = grid_nn_top2(g, seg, p.x, p.y, p.z, r, c, &bd, &d2nd, &pos, &t);
+  // points outside the scanned cells are farther than r minus the rounding of the cell-boundary test
+  float outer = r - 2e-7f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + r);
+  if (best < 0) {
+    // Nothing inside the gate ball.  Certify a whole cell size instead (3x3x3 cells), so that this point is not looked
+    // at again until it has moved that far; the nearest point found (beyond the gate) becomes the cached incumbent.
+    float d27, d27b;
+    float4 t27;
+    const int p27 = grid_scan27_top2(g, seg, p.x, p.y, p.z, &d27, &d27b, &t27);
+    if (d27 >= 0.f) {
+      outer = g.cs - 2e-7f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + g.cs);
+      if (p27 >= 0) {
+        best = __float_as_int(t27.w);
+        bd = d27;
+        d2nd = d27b;
+        pos = p27;
+        t = t27;
+      }
+      c = -1;  // the cached point, if any, was part of this scan
+    }
+  }
+  if (c >= 0) {  // merge the cached incumbent (skipped by the ball scan; it may lie outside the scanned ball)
+    const int bc = __float_as_int(tc.w);
+    if (bdc < bd || (bdc == bd && bc < best)) {
+      d2nd = bd;
+      bd = bdc;
+      best = bc;
+      pos = c;
+      t = tc;
+    } else {
+      d2nd = fminf(d2nd, bdc);
+    }
+  }
+  float lbn = fminf(sqrt_approx(d2nd), outer) * 0.9999f;
+  if (best >= 0 && !(__fmaf_rn(sqrt_approx(bd), 1.0001f, 1e-7f) < lbn)) {
+    // a winner that the new bound can never confirm is not worth caching: fold it into the bound over ALL points
+    lbn = fminf(lbn, sqrt_approx(bd) * 0.9999f);
+    pos = -1;
+  }
+  *out_lb = lbn;
+  *out_bd = bd;
+  *out_pos = pos;
+  *out_t = t;
+  return best;
+}
+
+template <bool FIRST>  // FIRST: nothing is cached yet (iteration 0), every point is queried in place (no work list)
+__global__ void __launch_bounds__(IT) k_icp_stream(float4* __restrict__ work, const int* __restrict__ count, int stride,
+                                                   const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
+                                                   float* __restrict__ lb, int* __restrict__ ci,
+                                                   int* __restrict__ wl, int* __restrict__ wlcount,
+                                                   double* __restrict__ partials, int* __restrict__ first_corr) {
+  __shared__ float M[16];
+  __shared__ double s_red[IT / 32][NRED];
+  __shared__ int s_wcnt[2][IT / 32];
+  const int seg = blockIdx.y;
+  if (st[seg].done) return;
+  const int n = count[seg];
+  const int apply = st[seg].apply_inc;
+  if (threadIdx.x < 16) M[threadIdx.x] = st[seg].inc_T[threadIdx.x];
+  __syncthreads();
+  const bool want_corr = first_corr != nullptr && st[seg].iterations == 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+  const int chunk = (((n + (int)gridDim.x - 1) / (int)gridDim.x + IT - 1) / IT) * IT;  // contiguous slice per block
+  const int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+  const float r = prm.search_r;
+  int nlist = 0, par = 0;
+  for (int base = lo; base < hi; base += IT, par ^= 1) {  // block-uniform trip count
+    const int i = base + threadIdx.x;
+    bool flag = false;
+    if (i < hi) {
+      const size_t gi = (size_t)seg * stride + i;
+      float4 p = work[gi];
+      float lbv = lb[gi];
+      const int c = ci[gi];
+      const bool fin = finite3(p.x, p.y, p.z);
+      if (apply && fin) {
+        const float3 q = xform_point(M, p.x, p.y, p.z);
+        lbv = lbv - __fmaf_rn(sqrt_approx(dist2_l2simple(q.x, q.y, q.z, p.x, p.y, p.z)), 1.00001f, 1e-9f);
+        p.x = q.x;
+        p.y = q.y;
+        p.z = q.z;
+        work[gi] = p;
+      }
+      if (!FIRST) lb[gi] = lbv;
+      if (!fin) {
+        if (want_corr) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = -1;
+        if (FIRST) lb[gi] = 0.f;
+      } else if (FIRST) {
+        float bd, lbn;
+        int pos;
+        float4 t;
+        const int best = icp_requery(g, seg, p, -1, r, &bd, &pos, &t, &lbn);
+        lb[gi] = lbn;
+        ci[gi] = pos;
+        const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
+        if (want_corr) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = ok ? best : -1;
+        if (ok) icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
+      } else {
+        bool valid;
+        float bd = INFINITY;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c >= 0) {
+          t = __ldg(&g.sorted[c]);
+          bd = dist2_l2simple(p.x, p.y, p.z, t.x, t.y, t.z);
+          valid = __fmaf_rn(sqrt_approx(bd), 1.0001f, 1e-7f) < lbv;
+        } else {
+          valid = lbv > r;
+        }
+        if (!valid) {
+          flag = true;
+        } else {
+          const bool ok = c >= 0 && !((double)bd > prm.max_dist_sqr);
+          if (want_corr) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = ok ? __float_as_int(t.w) : -1;
+          if (ok) icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
+        }
+      }
+    }
+    // ordered compaction of the flagged points of this tile
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_wcnt[par][wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < IT / 32; ++w) {
+      const int cw = s_wcnt[par][w];
+      before += (w < wid) ? cw : 0;
+      total += cw;
+    }
+    if (flag) wl[(size_t)seg * stride + lo + nlist + before + __popc(bal & ((1u << lane) - 1u))] = i;
+    nlist += total;
+  }
+  if (threadIdx.x == 0) wlcount[seg * gridDim.x + blockIdx.x] = nlist;
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < IT / 32; ++w) v += s_red[w][threadIdx.x];
+    partials[((size_t)seg * 2 * gridDim.x + blockIdx.x) * NRED + threadIdx.x] = v;
+  }
+}
+
+// exclusive scan of the per-block work-list counts of one segment (one CTA per segment; nblk <= a few thousand)
+__global__ void __launch_bounds__(1024) k_wl_offsets(const int* __restrict__ wlcount, int nblk, const IcpState* __restrict__ st,
+                                                     int* __restrict__ wloff) {
+  __shared__ int s_part[32];
+  __shared__ int s_carry;
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (st[seg].done) return;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    const int b = base + tid;
+    const int v = b < nblk ? wlcount[seg * nblk + b] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_part[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int w = s_part[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      s_part[lane] = wi - w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    if (b < nblk) wloff[seg * (nblk + 1) + b] = carry + s_part[wid] + incl - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + s_part[wid] + incl;
+    __syncthreads();
+  }
+  if (tid == 0) wloff[seg * (nblk + 1) + nblk] = s_carry;
+}
+
+__global__ void __launch_bounds__(IT) k_icp_rescan(float4* __restrict__ work, const int* __restrict__ count, int stride,
+                                                   const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
+                                                   float* __restrict__ lb, int* __restrict__ ci,
+                                                   const int* __restrict__ wl, const int* __restrict__ wloff,
+                                                   double* __restrict__ partials, int* __restrict__ first_corr) {
+  __shared__ double s_red[IT / 32][NRED];
+  const int seg = blockIdx.y;
+  if (st[seg].done) return;
+  const int n = count[seg];
+  const bool want_corr = first_corr != nullptr && st[seg].iterations == 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nblk = (int)gridDim.x;
+  const int chunk = (((n + nblk - 1) / nblk + IT - 1) / IT) * IT;
+  const int* off = wloff + seg * (nblk + 1);
+  const int total = off[nblk];
+  const float r = prm.search_r;
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+  // item t of the segment's concatenated (block-ordered) work list: a fixed item -> thread map, so sums stay reproducible
+  for (int t_ = blockIdx.x * IT + threadIdx.x; t_ < total; t_ += nblk * IT) {
+    int lo_b = 0, hi_b = nblk;  // largest b with off[b] <= t_
+    while (hi_b - lo_b > 1) {
+      const int mid = (lo_b + hi_b) >> 1;
+      if (__ldg(&off[mid]) <= t_) lo_b = mid; else hi_b = mid;
+    }
+    const int i = wl[(size_t)seg * stride + (size_t)lo_b * chunk + (t_ - __ldg(&off[lo_b]))];
+    const size_t gi = (size_t)seg * stride + i;
+    const float4 p = work[gi];  // already moved by the streaming pass
+    float bd, lbn;
+    int pos;
+    float4 t;
+    const int best = icp_requery(g, seg, p, ci[gi], r, &bd, &pos, &t, &lbn);
+    lb[gi] = lbn;
+    ci[gi] = pos;
+    const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
+    if (want_corr) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = ok ? best : -1;
+    if (ok) icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
+  }
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < IT / 32; ++w) v += s_red[w][threadIdx.x];
+    partials[((size_t)seg * 2 * gridDim.x + gridDim.x + blockIdx.x) * NRED + threadIdx.x] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" void rspcl_icp_reference_params(rspcl_icp_params* p) {
@@ -667,7 +959,13 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   const int nblk = blocks_per_seg(ctx, S, src->max_count_hint, IT);
   CU(ctx, scratch_alloc(ctx, &work, (size_t)S * wstride));
   CU(ctx, scratch_alloc(ctx, &st, (size_t)S));
-  CU(ctx, scratch_alloc(ctx, &partials, (size_t)S * nblk * NRED));
+  // global-memory path: certified-cache passes (k_icp_stream + k_icp_rescan) unless RSPCL_ICP_CACHE=0
+  const char* cache_env = getenv("RSPCL_ICP_CACHE");
+  const bool use_cache = !brute && !(cache_env && cache_env[0] == '0');
+  const int nblk_total = use_cache ? 2 * nblk : nblk;
+  float* g_lb = nullptr;
+  int *g_ci = nullptr, *g_wl = nullptr, *g_wlcount = nullptr, *g_wloff = nullptr;
+  CU(ctx, scratch_alloc(ctx, &partials, (size_t)S * nblk_total * NRED));
   CU(ctx, scratch_alloc(ctx, &d_prev, (size_t)S));
   CU(ctx, scratch_alloc(ctx, &n_active, 1));
   CU(ctx, scratch_alloc(ctx, &d_range, 1));
@@ -797,7 +1095,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         std::vector<long long> hd((size_t)S * cl * 8);
         CU(ctx, cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "persist dbg: S=%d cl=%d  [pair crank ns iters | phaseA waitA phaseB reduce+exchange solve head | total] kcycles\n", S, cl);
+        fprintf(stderr, "persist dbg: S=%d cl=%d  [pair crank ns iters | phaseA rescans(k) phaseB reduce+exchange solve head | total] kcycles\n", S, cl);
         for (int s = 0; s < S; ++s)
           for (int c = 0; c < cl; ++c) {
             const long long* D = &hd[((size_t)s * cl + c) * 8];
@@ -839,6 +1137,16 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   // between chunks (1, 1, 2, 4, 8, ... iterations), so the reference's one-iteration aligns cost one read-back.
   dim3 gstep(nblk, S);
   int done_iters = 0, chunk = 1, active = persist_done ? 0 : S;
+  if (use_cache && !persist_done) {
+    const size_t np = (size_t)S * wstride;
+    CU(ctx, scratch_alloc(ctx, &g_lb, np));
+    CU(ctx, scratch_alloc(ctx, &g_ci, np));
+    CU(ctx, scratch_alloc(ctx, &g_wl, np));
+    CU(ctx, scratch_alloc(ctx, &g_wlcount, (size_t)S * nblk));
+    CU(ctx, scratch_alloc(ctx, &g_wloff, (size_t)S * (nblk + 1)));
+    CU(ctx, cudaMemsetAsync(g_lb, 0, np * sizeof(float), ctx->stream));
+    CU(ctx, cudaMemsetAsync(g_ci, 0xFF, np * sizeof(int), ctx->stream));
+  }
   double prof_units = 0;  // source points per launch (all pairs; converged pairs exit early)
   if (ctx->prof_on && !persist_done) {
     std::vector<int> c(S);
@@ -849,26 +1157,44 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   while (done_iters < prm->max_iterations && active > 0) {
     const int todo = (chunk < prm->max_iterations - done_iters) ? chunk : prm->max_iterations - done_iters;
     for (int k = 0; k < todo; ++k) {
-      {
+      if (brute || !use_cache) {
         ProfScope prof(ctx, "k_icp_step", prof_units);
         if (brute)
           k_icp_step<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count,
                                                          tgt->stride, partials, d_first_corr);
-        else
+        else if (!use_cache)
           k_icp_step<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count,
                                                           tgt->stride, partials, d_first_corr);
+        LAUNCH_CHECK(ctx);
+      }
+      if (use_cache) {
+        {
+          ProfScope prof(ctx, "k_icp_stream", prof_units);
+          if (done_iters == 0 && k == 0)
+            k_icp_stream<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wlcount,
+                                                              partials, d_first_corr);
+          else
+            k_icp_stream<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wlcount,
+                                                               partials, d_first_corr);
+          LAUNCH_CHECK(ctx);
+        }
+        ProfScope prof(ctx, "k_icp_rescan", prof_units);
+        k_wl_offsets<<<S, 1024, 0, ctx->stream>>>(g_wlcount, nblk, st, g_wloff);
+        LAUNCH_CHECK(ctx);
+        k_icp_rescan<<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wloff,
+                                                    partials, d_first_corr);
         LAUNCH_CHECK(ctx);
       }
       ProfScope prof2(ctx, "k_icp_solve", (double)S);
       if (sharded) {
         // partial sums of this rank's shard -> NCCL all-reduce over NVLink -> identical solve on every rank
-        k_icp_sum_partials<<<S, 32, 0, ctx->stream>>>(partials, nblk, st, totals);
+        k_icp_sum_partials<<<S, 32, 0, ctx->stream>>>(partials, nblk_total, st, totals);
         LAUNCH_CHECK(ctx);
         int rcc = comm_allreduce_f64(ctx, totals, (size_t)S * NRED);
         if (rcc) return rcc;
         k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, totals, 1, dp, n_active);
       } else {
-        k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, partials, nblk, dp, n_active);
+        k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, partials, nblk_total, dp, n_active);
       }
       LAUNCH_CHECK(ctx);
     }
@@ -878,6 +1204,14 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     if (done_iters > 1) chunk *= 2;
   }
 
+  if (use_cache && !persist_done && getenv("RSPCL_ICP_DBG")) {  // debug: size of the last iteration's rescan list
+    for (int sg = 0; sg < S && sg < 4; ++sg) {
+      int tot = -1;
+      CU(ctx, cudaMemcpyAsync(&tot, g_wloff + (size_t)sg * (nblk + 1) + nblk, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(ctx, cudaStreamSynchronize(ctx->stream));
+      fprintf(stderr, "icp dbg: seg %d: %d points re-queried in the last iteration (nblk %d)\n", sg, tot, nblk);
+    }
+  }
   // results + aligned output (Registration::align: output = final applied to the original source)
   std::vector<IcpState> hst(S);
   int range = 0;
@@ -909,6 +1243,11 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   scratch_free(ctx, d_T);
   scratch_free(ctx, totals);
   scratch_free(ctx, perm);
+  scratch_free(ctx, g_lb);
+  scratch_free(ctx, g_ci);
+  scratch_free(ctx, g_wl);
+  scratch_free(ctx, g_wlcount);
+  scratch_free(ctx, g_wloff);
   if (rc) return rc;
   if (range) RSPCL_FAIL(ctx, RSPCL_ERR_RANGE, "icp_align: target coordinates exceed the grid key range (+-32767 cells of %g m)", cs);
   return RSPCL_OK;

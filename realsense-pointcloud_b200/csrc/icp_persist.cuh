@@ -312,7 +312,7 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
       }
       P_TICK(0);
       __syncthreads();
-      P_TICK(1);
+      if (dbg && tid == 0) tph[1] += S.nwork;  // debug: rescans
       // ---------------- phase B: 8 lanes per work item, one neighbour cell each, merged with xor shuffles
       const int nwork = S.nwork;
       for (int jb = wid * 4; jb < nwork; jb += P_WARPS * 4) {  // warp-uniform trip count (full-mask shuffles below)
@@ -437,7 +437,7 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
       __syncthreads();
     }
     P_TICK(3);
-    if (tid == 0) icp_solve_pair(&S.st, S.tot, prm, &S.flags[1]);
+    if (wid == 0) icp_solve_pair(&S.st, S.tot, prm, &S.flags[1], lane);
     P_TICK(4);
     __syncthreads();
     if (S.st.done) break;

@@ -397,3 +397,78 @@ def test_frames_with_holes_and_nans(ctx, pair2):
     assert res[0]["n_corr"] == o["n_corr"] and res[0]["converged"] == o["converged"]
     ang, tr = pose_err(res[0]["T"], o["T"])
     assert ang < 1e-4 and tr < 1e-4
+
+
+# ------------------------------------------------------------------ global-memory ICP path (certified-cache passes)
+@pytest.fixture
+def global_path(monkeypatch):
+    """Force icp_align off the shared-memory persistent kernel (what clouds > 12288 target points take anyway)."""
+    monkeypatch.setenv("RSPCL_ICP_PERSIST", "0")
+    yield monkeypatch
+
+
+def test_icp_global_path_matches_oracle_and_legacy(ctx, pair2, global_path):
+    fr, _ = pair2
+    tgt, src = edge_pair(fr)
+    guess = np.eye(4)
+    guess[:3, :3] = gen_scene.rot_y(-0.523599)
+    gp, op = forced(30)
+    o = orc.icp_align(src, tgt, op, guess=guess, want_first_corr=True)
+    out = {}
+    for cache in ("1", "0"):  # k_icp_stream + k_icp_rescan vs the per-iteration full scan (k_icp_step)
+        global_path.setenv("RSPCL_ICP_CACHE", cache)
+        res, _, fc = R.icp_align(ctx, ctx.upload([src]), ctx.upload([tgt]), gp, guess=guess, want_aligned=False, want_first_corr=True)
+        assert np.array_equal(fc, o["first_corr"])
+        r = res[0]
+        assert r["iterations"] == o["iterations"] == 30
+        ang, tr = pose_err(r["T"], o["T"])
+        assert ang < 1e-4 and tr < 1e-4, (cache, ang, tr)
+        assert abs(r["n_corr"] - o["n_corr"]) <= max(3, o["n_corr"] // 200)
+        out[cache] = r
+    # both GPU paths take the exact nearest neighbour every iteration: same correspondences, same sums up to fp64 order
+    assert out["1"]["n_corr"] == out["0"]["n_corr"]
+    assert np.abs(out["1"]["T"] - out["0"]["T"]).max() < 1e-6
+
+
+def test_icp_global_path_batch_mixed_states(ctx, global_path):
+    rng = np.random.default_rng(29)
+    tgt = rand_cloud(rng, 4000, 0.5)
+    s_ok = orc.transform(tgt[::2], np.linalg.inv(rigid(rng, 0.002, 0.001)))
+    s_far = tgt[::3].copy()
+    s_far["x"] += 10.0
+    s_nan = s_ok.copy()
+    s_nan["y"][::7] = np.nan
+    srcs = [s_ok, s_far, s_nan, np.zeros(0, R.POINT)]
+    gp, op = forced(12)
+    res, aligned, fc = R.icp_align(ctx, ctx.upload(srcs), ctx.upload([tgt]), gp, want_first_corr=True)
+    al = aligned.download()
+    off = 0
+    for k, s in enumerate(srcs):
+        o = orc.icp_align(s, tgt, op, want_first_corr=True)
+        assert np.array_equal(fc[off:off + len(s)], o["first_corr"]), k
+        off += len(s)
+        assert res[k]["converged"] == o["converged"] and res[k]["state"] == o["state"] and res[k]["iterations"] == o["iterations"], k
+        assert res[k]["n_corr"] == o["n_corr"], k
+        if o["converged"]:
+            ang, tr = pose_err(res[k]["T"], o["T"])
+            assert ang < 1e-4 and tr < 1e-4
+        fin = np.isfinite(s["y"])
+        assert np.array_equal(al[k][fin].view(np.uint32), orc.transform(s, res[k]["T"])[fin].view(np.uint32))
+
+
+def test_icp_large_target_takes_global_path(ctx):
+    """A target above the shared-memory capacity (12288 points) goes to the grid path without any env override."""
+    rng = np.random.default_rng(31)
+    tgt = rand_cloud(rng, 40000, 0.5)
+    T = rigid(rng, 0.002, 0.002)
+    src = orc.transform(tgt[::3], np.linalg.inv(T))
+    kw = dict(max_iterations=15, max_corr_dist=0.02, transformation_epsilon=-1.0, euclidean_fitness_epsilon=-1e300,
+              mse_threshold_absolute=-1.0)
+    res, _, fc = R.icp_align(ctx, ctx.upload([src]), ctx.upload([tgt]), R.icp_params(**kw), want_aligned=False, want_first_corr=True)
+    o = orc.icp_align(src, tgt, orc.icp_params(**kw), want_first_corr=True)
+    assert np.array_equal(fc, o["first_corr"])
+    assert res[0]["n_corr"] == o["n_corr"] and res[0]["iterations"] == 15
+    ang, tr = pose_err(res[0]["T"], o["T"])
+    assert ang < 1e-4 and tr < 1e-4
+    ang, tr = pose_err(res[0]["T"], T)
+    assert ang < 1e-3 and tr < 1e-3
