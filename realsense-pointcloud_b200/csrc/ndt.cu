@@ -511,10 +511,122 @@ __device__ void angle_derivatives(const double* p, NdtEval* E) {
 #undef SET3
 }
 
+// Newton step H dp = -g.  Near the optimum the NDT Hessian is symmetric and definite (negative definite for PCL's
+// score, which is maximised): an unrolled LDL^T of +-H in registers (6 divisions) gives the same dp as the
+// pseudo-inverse to rounding.  Anything else (a pivot that is not clearly of the common sign) takes the Jacobi
+// pseudo-inverse that restates PCL's JacobiSVD solve, rank threshold included.
+__device__ bool solve6_ldlt(const double* A_in, const double* g_in, double* x) {
+  double L[36], D[6], A[36], g[6];
+  const double sgn = A_in[0] < 0.0 ? -1.0 : 1.0;  // solve (sgn H) dp = -(sgn g)
+#pragma unroll
+  for (int i = 0; i < 36; ++i) A[i] = sgn * A_in[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) g[i] = sgn * g_in[i];
+  double maxd = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) maxd = fmax(maxd, fabs(A[i * 6 + i]));
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
+    if (!(d > 1e-9 * maxd)) return false;
+    D[j] = d;
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i * 6 + k] * L[j * 6 + k] * D[k];
+      L[i * 6 + j] = v * inv;
+    }
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = -g[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= L[i * 6 + k] * y[k];
+    y[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[i] /= D[i];
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double v = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v -= L[k * 6 + i] * x[k];
+    x[i] = v;
+  }
+  return true;
+}
+
+// Indefinite but well-conditioned Hessians (far from the optimum, fine voxels): Gaussian elimination with partial
+// pivoting, rows swapped by predicated moves so that every index stays static (registers).  Refuses (-> pseudo-inverse)
+// when a pivot falls below 1e-7 of the largest entry.
+__device__ bool solve6_gepp(const double* A_in, const double* g, double* x) {
+  double A[36], b[6];
+  double amax = 0;
+#pragma unroll
+  for (int i = 0; i < 36; ++i) {
+    A[i] = A_in[i];
+    amax = fmax(amax, fabs(A[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b[i] = -g[i];
+  if (!(amax > 0.0)) return false;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    int piv = j;
+    double pv = fabs(A[j * 6 + j]);
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      const double v = fabs(A[i * 6 + j]);
+      if (v > pv) {
+        pv = v;
+        piv = i;
+      }
+    }
+    if (!(pv > 1e-7 * amax)) return false;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      if (i == piv) {
+#pragma unroll
+        for (int k = j; k < 6; ++k) {
+          const double t = A[j * 6 + k];
+          A[j * 6 + k] = A[i * 6 + k];
+          A[i * 6 + k] = t;
+        }
+        const double t = b[j];
+        b[j] = b[i];
+        b[i] = t;
+      }
+    }
+    const double inv = 1.0 / A[j * 6 + j];
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      const double f = A[i * 6 + j] * inv;
+#pragma unroll
+      for (int k = j + 1; k < 6; ++k) A[i * 6 + k] -= f * A[j * 6 + k];
+      b[i] -= f * b[j];
+    }
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v -= A[i * 6 + k] * x[k];
+    x[i] = v / A[i * 6 + i];
+  }
+  return true;
+}
+
 __device__ void solve_newton(const double* H, const double* g, double* dp) {
   double S[36], w[6], V[36];
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j < 6; ++j) S[i * 6 + j] = 0.5 * (H[i * 6 + j] + H[j * 6 + i]);
+  if (solve6_ldlt(S, g, dp)) return;
+  if (solve6_gepp(S, g, dp)) return;
   jacobi_eigh<6>(S, w, V);
   double wmax = 0;
   for (int i = 0; i < 6; ++i) wmax = fmax(wmax, fabs(w[i]));
@@ -604,22 +716,8 @@ __global__ void k_ndt_init(NdtState* __restrict__ st, NdtEval* __restrict__ ev, 
   S->step_iterations = 0;
 }
 
-__global__ void __launch_bounds__(32) k_ndt_control(NdtState* __restrict__ st, NdtEval* __restrict__ ev,
-                                                    const double* __restrict__ partials, int nblk, NdtCtl ctl,
-                                                    int* __restrict__ n_active) {
-  const int seg = blockIdx.x;
-  NdtState* S = &st[seg];
-  NdtEval* E = &ev[seg];
-  if (S->done) return;
-  const int lane = threadIdx.x;
-  __shared__ double sums[NACC];
-  double v = 0;
-  if (lane < NACC)
-    for (int b = 0; b < nblk; ++b) v += partials[((size_t)seg * nblk + b) * NACC + lane];
-  if (lane < NACC) sums[lane] = v;
-  __syncwarp();
-  if (lane != 0) return;
-
+// Newton / More-Thuente controller for one pair (one thread); returns true when the pair has finished.
+__device__ bool ndt_control_step(NdtState* S, NdtEval* E, const double* sums, const NdtCtl& ctl) {
   const double mu = 1.e-4, nu = 0.9;
   const double step_max = ctl.step_size, step_min = ctl.eps / 2;
   // ---- consume the evaluation that just ran
@@ -697,13 +795,13 @@ __global__ void __launch_bounds__(32) k_ndt_control(NdtState* __restrict__ st, N
         E->want_hessian = 0;
         E->hessian_only = 0;
         S->phase = PH_MT_LOOP;
-        return;
+        return false;
       }
       if (S->step_iterations) {  // computeHessian at the accepted step (angle derivatives are already those of x_t)
         E->want_hessian = 1;
         E->hessian_only = 1;
         S->phase = PH_MT_HESS;
-        return;
+        return false;
       }
       goto_after = true;
     }
@@ -761,14 +859,55 @@ __global__ void __launch_bounds__(32) k_ndt_control(NdtState* __restrict__ st, N
       E->want_hessian = 1;
       E->hessian_only = 0;
       S->phase = PH_MT_FIRST;
-      return;
+      return false;
     }
   }
   // finished (converged or NaN step)
   S->done = 1;
   E->active = 0;
-  atomicSub(n_active, 1);
+  return true;
 }
+
+// One warp per pair: the lanes combine the CTA partials (fixed block order) and stage the pair's state in shared
+// memory, lane 0 runs the controller on the shared copy (no dependent global round trips), the lanes write it back.
+__global__ void __launch_bounds__(32) k_ndt_control(NdtState* __restrict__ st, NdtEval* __restrict__ ev,
+                                                    const double* __restrict__ partials, int nblk, NdtCtl ctl,
+                                                    int* __restrict__ n_active) {
+  const int seg = blockIdx.x;
+  if (st[seg].done) return;
+  const int lane = threadIdx.x;
+  __shared__ double sums[NACC];
+  __shared__ NdtState sS;
+  static_assert(sizeof(NdtState) % 4 == 0, "NdtState is copied as 32-bit words");
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&st[seg]);
+    unsigned* dst = reinterpret_cast<unsigned*>(&sS);
+    for (int i = lane; i < (int)(sizeof(NdtState) / 4); i += 32) dst[i] = src[i];
+  }
+  if (lane < NACC) {
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;  // four independent chains; combined in a fixed order
+    int b = 0;
+    for (; b + 3 < nblk; b += 4) {
+      v0 += partials[((size_t)seg * nblk + b) * NACC + lane];
+      v1 += partials[((size_t)seg * nblk + b + 1) * NACC + lane];
+      v2 += partials[((size_t)seg * nblk + b + 2) * NACC + lane];
+      v3 += partials[((size_t)seg * nblk + b + 3) * NACC + lane];
+    }
+    for (; b < nblk; ++b) v0 += partials[((size_t)seg * nblk + b) * NACC + lane];
+    sums[lane] = (v0 + v1) + (v2 + v3);
+  }
+  __syncwarp();
+  bool finished = false;
+  if (lane == 0) finished = ndt_control_step(&sS, &ev[seg], sums, ctl);
+  __syncwarp();
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&sS);
+    unsigned* dst = reinterpret_cast<unsigned*>(&st[seg]);
+    for (int i = lane; i < (int)(sizeof(NdtState) / 4); i += 32) dst[i] = src[i];
+  }
+  if (finished) atomicSub(n_active, 1);
+}
+
 
 __global__ void k_ndt_gather_T(const NdtState* __restrict__ st, float* __restrict__ T, int n_seg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -957,6 +1096,7 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         k_ndt_eval<<<ge, NT, 0, ctx->stream>>>(src->pts, src->count, src->stride, ev, G, d1, d2, partials);
         LAUNCH_CHECK(ctx);
       }
+      ProfScope prof_c(ctx, "k_ndt_control", (double)S);
       if (sharded) {
         k_ndt_sum_partials_active<<<S, 32, 0, ctx->stream>>>(partials, nblk, ev, totals);
         LAUNCH_CHECK(ctx);
