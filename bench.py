@@ -208,6 +208,30 @@ def workload_config(a, frames):
             "parallelism": "pair-sharded x%d (independent sweeps, no collective)" % a.gpus}
 
 
+def bind_to_gpu_numa_node(torch, dev):
+    """Best effort: run this rank's host threads (and first-touch its pinned buffers) on the CPUs next to its GPU, so that
+    N ranks do not all stream their frames through one socket's memory controller.  Returns a short description."""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return "bound to %d of %d allowed CPUs local to %s" % (len(use), len(allowed), bus)
+        return "no binding (%d local CPUs allowed of %d)" % (len(use), len(allowed))
+    except Exception as e:  # sysfs layout differs / not permitted: run unbound
+        return "no binding (%s)" % type(e).__name__
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     a = parse()
@@ -230,6 +254,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
+    numa = bind_to_gpu_numa_node(torch, dev)
     ctx = R.Context(dev)
 
     F = a.frames
@@ -437,7 +462,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": (n_pairs + len(chunks)) * NPX * 32,
                     "d2h_bytes_per_step": n_pairs * NPX * 32 + n_pairs * 160, "ms_per_step": ms_e2e / a.steps,
-                    "pipeline": "%d chunks over %d contexts (streams), pinned host buffers" % (len(chunks), n_ctx)},
+                    "pipeline": "%d chunks over %d contexts (streams), pinned host buffers" % (len(chunks), n_ctx),
+                    "host_numa": numa},
             "gpu_launches": int(l1 - l0),
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -586,8 +586,11 @@ __global__ void k_copy_work(const float4* __restrict__ src, const int* __restric
                             float4* __restrict__ work, int stride_work) {
   const int seg = blockIdx.y;
   const int n = count[seg];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    work[(size_t)seg * stride_work + i] = src[(size_t)seg * stride_src + i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = src[(size_t)seg * stride_src + i];
+    p.w = __int_as_float(i);  // original index (rgba is not needed by the iterations)
+    work[(size_t)seg * stride_work + i] = p;
+  }
 }
 
 // cell key of every source point (for the spatial sort of the working cloud: neighbouring lanes then query
@@ -981,10 +984,12 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   // Working cloud = source in SPATIAL order (radix sort by cell key), original index kept in .w: neighbouring lanes
   // then probe neighbouring cells (coalesced / cached probes, far less divergence).  Sums are order-independent up to
   // fp64 rounding; first_corr and the aligned output are written in original order.
+  // (The persistent kernel keeps its target in shared memory and, with the certified cache, scans only a few points per
+  // iteration, so it takes the source in its original order and skips the sort: ~1.2 ms per 64-pair step.)
   const float sort_inv_cs = brute ? 10.0f : 1.0f / (float)(prm->max_corr_dist * 4.1);
   int* perm = nullptr;
   const int pstride = src->max_count_hint > 0 ? src->max_count_hint : 1;
-  {
+  auto build_sorted_work = [&]() -> int {
     const long long N = (long long)S * pstride;
     unsigned long long *keys = nullptr, *tkeys = nullptr;
     int* tvals = nullptr;
@@ -1002,17 +1007,29 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     scratch_free(ctx, keys);
     scratch_free(ctx, tkeys);
     scratch_free(ctx, tvals);
+    return RSPCL_OK;
+  };
+  const bool sharded = ctx->sharded_call && ctx->nccl_comm && ctx->nranks > 1;
+  bool want_persist = false;
+  {
+    const char* env = getenv("RSPCL_ICP_PERSIST");
+    want_persist = !(env && env[0] == '0') && !sharded && !brute && tgt->max_count_hint <= P_NTMAX &&
+                   src->max_count_hint > 0 && src->max_count_hint < 65536;
+  }
+  if (want_persist) {
+    k_copy_work<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, work, wstride);
+    LAUNCH_CHECK(ctx);
+  } else {
+    const int rcs = build_sorted_work();
+    if (rcs) return rcs;
   }
 
   // ---- persistent shared-memory path: one cluster per pair, all iterations in one launch (icp_persist.cuh)
   bool persist_done = false;
-  const bool sharded = ctx->sharded_call && ctx->nccl_comm && ctx->nranks > 1;
   double* totals = nullptr;
   if (sharded) CU(ctx, scratch_alloc(ctx, &totals, (size_t)S * NRED));
   {
-    const char* env = getenv("RSPCL_ICP_PERSIST");
-    const bool want = !(env && env[0] == '0') && !sharded;
-    if (want && !brute && tgt->max_count_hint <= P_NTMAX && src->max_count_hint > 0 && src->max_count_hint < 65536) {
+    if (want_persist) {
       int* d_status = nullptr;
       CU(ctx, scratch_alloc(ctx, &d_status, (size_t)S));
       CU(ctx, cudaMemsetAsync(d_status, 0, (size_t)S * sizeof(int), ctx->stream));
@@ -1119,8 +1136,8 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       } else {  // a target did not fit the shared-memory grid: redo the whole batch on the global-memory path
         k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, S);
         LAUNCH_CHECK(ctx);
-        k_copy_work_perm<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, perm, pstride, work, wstride);
-        LAUNCH_CHECK(ctx);
+        const int rcs = build_sorted_work();
+        if (rcs) return rcs;
       }
     }
   }
