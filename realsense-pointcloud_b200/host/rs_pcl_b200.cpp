@@ -3,6 +3,9 @@
 //   rs_pcl_b200 [--dataset DIR] [--scheme ndt|icp|incremental] --registration <prefix> [deg] <N>
 //       loads DIR/<prefix>-<i>.pcd (i < N), runs the scheme (default: NDT edge-based, like main.cpp:208,218), writes
 //       DIR/<prefix>-registration (main.cpp:87, no suffix) and prints the per-frame transforms as one JSON line.
+//       --imu FILE: IMU trace ("ts_ms kind x y z" rows, kind 0 = gyro, 1 = accel) followed by a line "frames t0 t1 ..";
+//       the angle triples of the complementary filter (rotation_estimator.hpp) replace the fixed-degree guess, as in
+//       the reference's capture modes (main.cpp:129).
 //   rs_pcl_b200 [--dataset DIR] --edges <file>
 //       extract_edge_features of DIR/<file> (main.cpp:58-62); prints the edge count, writes DIR/<file>.edges.pcd.
 // The GL viewer loops of the reference (main.cpp:65-73,90-98) and the capture modes are out of scope.
@@ -25,11 +28,12 @@ static void print_json(const std::vector<rspcl::Matrix4f>& T, const std::vector<
 
 int main(int argc, char** argv) {
   try {
-    std::string dir = "dataset", scheme = "ndt";
+    std::string dir = "dataset", scheme = "ndt", imu_path;
     std::vector<std::string> a;
     for (int i = 1; i < argc; ++i) {
       if (!std::strcmp(argv[i], "--dataset") && i + 1 < argc) dir = argv[++i];
       else if (!std::strcmp(argv[i], "--scheme") && i + 1 < argc) scheme = argv[++i];
+      else if (!std::strcmp(argv[i], "--imu") && i + 1 < argc) imu_path = argv[++i];
       else a.push_back(argv[i]);
     }
     if (a.size() >= 2 && a[0] == "--edges") {
@@ -60,17 +64,40 @@ int main(int argc, char** argv) {
       rgb_point_cloud_pointer result;
       std::vector<rspcl::Matrix4f> T;
       std::vector<int> acc;
+      std::vector<rs_float3> thetas;
+      if (!imu_path.empty()) {
+        std::ifstream f(imu_path);
+        if (!f) throw rspcl::Error("cannot open " + imu_path);
+        std::vector<ImuSample> trace;
+        std::vector<double> frame_ts;
+        std::string tok;
+        while (f >> tok) {
+          if (tok == "frames") {
+            double t;
+            while (f >> t) frame_ts.push_back(t);
+            break;
+          }
+          ImuSample s;
+          s.ts_ms = std::atof(tok.c_str());
+          if (!(f >> s.kind >> s.v.x >> s.v.y >> s.v.z)) throw rspcl::Error("bad IMU row in " + imu_path);
+          trace.push_back(s);
+        }
+        if ((int)frame_ts.size() != frames) throw rspcl::Error("IMU trace needs one timestamp per frame");
+        thetas = thetas_from_imu_trace(trace, frame_ts);
+      }
       if (scheme == "incremental") {
         IncrementalICP s;
         result = s.registration(clouds);
         T = s.transforms;
         acc.assign(T.size(), 1);
       } else if (scheme == "icp") {
-        ICPEdgeBasedRegistration s(rads);
+        ICPEdgeBasedRegistration s_imu(thetas), s_fix(rads);
+        ICPEdgeBasedRegistration& s = thetas.empty() ? s_fix : s_imu;
         result = s.registration(clouds);
         T = s.transforms, acc = s.accepted;
       } else {
-        NDTEdgeBasedRegistration s(rads);
+        NDTEdgeBasedRegistration s_imu(thetas), s_fix(rads);
+        NDTEdgeBasedRegistration& s = thetas.empty() ? s_fix : s_imu;
         result = s.registration(clouds);
         T = s.transforms, acc = s.accepted;
       }
@@ -78,7 +105,7 @@ int main(int argc, char** argv) {
       print_json(T, acc, result->size());
       return 0;
     }
-    std::fprintf(stderr, "usage: rs_pcl_b200 [--dataset DIR] [--scheme ndt|icp|incremental] --registration <prefix> [deg] <N>\n"
+    std::fprintf(stderr, "usage: rs_pcl_b200 [--dataset DIR] [--scheme ndt|icp|incremental] [--imu FILE] --registration <prefix> [deg] <N>\n"
                          "       rs_pcl_b200 [--dataset DIR] --edges <file>\n");
     return 2;
   } catch (const std::exception& e) {

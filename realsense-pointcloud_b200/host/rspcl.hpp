@@ -114,6 +114,80 @@ struct rs_float3 {
   void add(float t1, float t2, float t3) { x += t1, y += t2, z += t3; }
 };
 
+// ------------------------------------------------------------------ IMU initial-guess front end
+// Host-side complementary filter that turns gyro / accelerometer samples into the per-frame angle triple the scheme
+// constructors take (rotation_estimator.hpp:22-79: gyro integration between samples, accelerometer tilt blended with
+// weight 1 - alpha, yaw initialised to PI because gravity says nothing about it).  `rs_vector` stands in for
+// librealsense's rs2_vector; timestamps are milliseconds like rs2_frame::get_timestamp().  Not thread-safe: the
+// reference guards theta with a mutex because its callbacks run on the sensor thread, a replayed trace does not.
+struct rs_vector {
+  float x, y, z;
+};
+
+class RotationEstimator {
+ public:
+  explicit RotationEstimator(float alpha = 0.98f) : alpha_(alpha) {}
+
+  void process_gyro(rs_vector gyro, double ts_ms) {
+    if (first_) {  // until the first accelerometer sample fixes the initial pose only the clock is tracked
+      last_ts_gyro_ = ts_ms;
+      return;
+    }
+    const float dt = static_cast<float>((ts_ms - last_ts_gyro_) / 1000.0);
+    last_ts_gyro_ = ts_ms;
+    // gyro x/y/z = pitch/yaw/roll rates; theta.x <- -roll, theta.y <- -yaw, theta.z <- +pitch (rotation_estimator.hpp:45)
+    theta_.add(-(gyro.z * dt), -(gyro.y * dt), gyro.x * dt);
+  }
+
+  void process_accel(rs_vector accel) {
+    // the reference calls the C double atan2 / sqrt on float arguments and narrows the result
+    const float az = static_cast<float>(std::atan2(static_cast<double>(accel.y), static_cast<double>(accel.z)));
+    const float ax = static_cast<float>(std::atan2(static_cast<double>(accel.x),
+                                                   std::sqrt(static_cast<double>(accel.y * accel.y + accel.z * accel.z))));
+    if (first_) {
+      first_ = false;
+      theta_.x = ax;
+      theta_.y = 3.14159265358979323846f;  // PI (utils.hpp)
+      theta_.z = az;
+    } else {
+      theta_.x = theta_.x * alpha_ + ax * (1.0f - alpha_);
+      theta_.z = theta_.z * alpha_ + az * (1.0f - alpha_);
+    }
+  }
+
+  rs_float3 get_theta() const { return theta_; }
+
+ private:
+  rs_float3 theta_{0.f, 0.f, 0.f};
+  float alpha_;
+  bool first_ = true;
+  double last_ts_gyro_ = 0;
+};
+
+// Replays a recorded IMU trace and samples theta at each frame's capture time -- what capture.hpp does live when it
+// pushes estimator.get_theta() next to every captured cloud.  Trace rows: {ts_ms, kind (0 gyro, 1 accel), x, y, z},
+// ascending in time; a frame takes the estimate after all samples with ts <= its timestamp.
+struct ImuSample {
+  double ts_ms;
+  int kind;
+  rs_vector v;
+};
+
+inline std::vector<rs_float3> thetas_from_imu_trace(const std::vector<ImuSample>& trace, const std::vector<double>& frame_ts_ms,
+                                                    float alpha = 0.98f) {
+  RotationEstimator est(alpha);
+  std::vector<rs_float3> out;
+  std::size_t k = 0;
+  for (double t : frame_ts_ms) {
+    for (; k < trace.size() && trace[k].ts_ms <= t; ++k) {
+      if (trace[k].kind == 0) est.process_gyro(trace[k].v, trace[k].ts_ms);
+      else est.process_accel(trace[k].v);
+    }
+    out.push_back(est.get_theta());
+  }
+  return out;
+}
+
 namespace rspcl {
 
 // ------------------------------------------------------------------ device context + RAII cloud handles

@@ -84,3 +84,26 @@ def test_edges_cli(dataset):
     assert res["edge_points"] == len(e)
     got, _, _ = gen_scene.read_pcd(os.path.join(d, "synth-1.pcd.edges.pcd"))
     assert np.array_equal(got, e)
+
+
+def test_registration_cli_imu_guess(dataset, tmp_path):
+    """--imu: a recorded gyro/accel trace (pure yaw of -30 deg between frames, sign convention theta.y -= gyro.y dt)
+    replaces the fixed-degree guess; the NDT scheme's R_y(-theta.y) (ndt:79) must land on the same registration."""
+    d, fr, Tgt = dataset
+    rows, t = [], 0.0
+    rows.append("%.3f 1 0 -9.81 0" % 0.0)  # first accelerometer sample fixes the initial pose
+    rate = -0.523599  # rad/s; one frame per second; guess = R_y(-(theta_k.y - theta_0.y)) = R_y(k * rate)
+    for i in range(1, 2001):
+        t = i * 1.0
+        rows.append("%.3f 0 0 %.9g 0" % (t, rate))
+    path = tmp_path / "imu.txt"
+    path.write_text("\n".join(rows) + "\nframes 0.5 1000.5 2000.5\n")
+    res = run(["--dataset", d, "--scheme", "ndt", "--imu", str(path), "--registration", "synth", "3"])
+    ref = run(["--dataset", d, "--scheme", "ndt", "--registration", "synth", "3"])
+    assert res["accepted"] == [1, 1, 1]
+    for k in range(3):
+        T = np.array(res["transforms"][k]).reshape(4, 4)
+        ang, tr = pose_err(T, Tgt[k])
+        assert ang < 0.03 and tr < 0.05, (k, ang, tr)
+        ang, tr = pose_err(T, np.array(ref["transforms"][k]).reshape(4, 4))
+        assert ang < 0.02 and tr < 0.03, (k, ang, tr)
