@@ -10,8 +10,10 @@ settings: -30 deg initial guess, 50 forced coarse + 50 forced fine iterations, 1
   e2e    : the same step through the C ABI with HOST buffers: pinned pcl::PointXYZRGB (32 B/pt) frames uploaded and the
            transformed full clouds downloaded inside the timed region.
   roofline: the ICP correspondence+reduction kernel (k_icp_persist: all iterations of a batch of pairs in one launch;
-           k_icp_step on the global-memory fallback), algorithmic bytes = 32 B per source point per iteration,
+           k_icp_stream on the global-memory path), algorithmic bytes = 32 B per source point per iteration,
            timed with CUDA events bracketing each launch in one extra, untimed-for-`value` step.
+  ndt    : (rank 0, N=1) BASELINE configs[2] on the side: one 1280x720 pair, 0.05 m voxels -> ms per NDT iteration and per
+           derivative evaluation (the metric also names "ms per ICP/NDT iteration").
   cpu_baseline: the oracle (CPU port of the reference's PCL path) on a bounded sample of the same sweep, 1 thread.
   --impl reference: the oracle with all host threads (one pair per thread) -- the reference arm.
 
@@ -48,6 +50,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--cpu-pairs", type=int, default=24, help="pairs in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ndt", action="store_true", help="skip the side measurement of configs[2] (NDT, 1280x720)")
     ap.add_argument("--e2e-contexts", type=int, default=4)
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--e2e-lock", default="nosync", choices=["sync", "nosync", "none"],
@@ -435,8 +438,36 @@ def main():
                 "share_of_step": ki["ms"] / ms_prof if ms_prof > 0 else None,
                 "units": "source points x executed iterations (32 B each: 16 R source + 16 R matched target)",
                 "note": "persistent kernel: the target grid lives in shared memory and the working cloud in L2, so DRAM traffic "
-                        "is far below the algorithmic bytes; the kernel is bound by LDS latency / issue slots and by the slowest "
-                        "pair of the batch, not by HBM (SURVEY H3)"}
+                        "is ~2 % of the algorithmic bytes; the kernel is bound by the serial chain of one ICP iteration (stream, "
+                        "re-query, reduce, cluster exchange, solve) on the slowest pair of the batch, not by HBM (SURVEY H3). "
+                        "The HBM-bound regime (one 25 M-point pair, k_icp_stream: 4.5 TB/s of DRAM traffic, 27 % in algorithmic "
+                        "bytes) is in profiles/r01_v3_summary.md"}
+
+    # ---- side measurement (rank 0, N=1): BASELINE configs[2], edge-based NDT on one 1280x720 pair, 0.05 m voxels
+    ndt_leg = None
+    if rank == 0 and world == 1 and not a.no_ndt:
+        W2, H2 = 1280, 720
+        fr2, T2 = gen_scene.make_sweep(3, 2, W2, H2, noise_scale=0.2)
+        d2 = ctx.upload(list(fr2), W2, H2)
+        v2 = R.voxel_approx(ctx, R.edge_extract(ctx, d2)).download()
+        s2, t2 = ctx.upload([v2[1]]), ctx.upload([v2[0]])
+        p2 = R.ndt_params(resolution=0.05)
+        R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
+        ctx.profile_reset()
+        ctx.profile(True)
+        ctx.timer_start()
+        r2, _ = R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
+        ms2 = ctx.timer_stop()
+        ctx.profile(False)
+        ke, kc = ctx.profile_get("k_ndt_eval"), ctx.profile_get("k_ndt_control")
+        ang2, tr2 = pose_err(r2[0]["T"], gen_scene.pairwise_gt(T2, 1))
+        ndt_leg = {"workload": "configs[2]: edge-based NDT, one 1280x720 pair (921,600 points per frame), 0.05 m voxels, step 0.1, eps 0.01",
+                   "edge_points_src_tgt": [int(len(v2[1])), int(len(v2[0]))], "iterations": r2[0]["iterations"],
+                   "derivative_evals": r2[0]["n_derivative_evals"], "converged": bool(r2[0]["converged"]),
+                   "ms_align": ms2, "ms_per_ndt_iteration": ms2 / max(r2[0]["iterations"], 1),
+                   "ms_per_derivative_eval": ke["ms"] / max(ke["launches"], 1),
+                   "ms_per_control_step": kc["ms"] / max(kc["launches"], 1),
+                   "err_vs_ground_truth_rad_m": [ang2, tr2]}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle, one thread, bounded sample of the same sweep
     cpu = None
@@ -468,6 +499,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernels_ms_per_step": {k: v["ms"] for k, v in kern.items() if v["launches"]},
+            "ndt": ndt_leg,
             "ms_per_icp_iteration": (kern[dom]["ms"] + kern["k_icp_solve"]["ms"]) / (2.0 * a.iters if dom == "k_icp_persist" else max(kern[dom]["launches"], 1)),
             "check": {"pairs_converged": n_conv, "max_err_vs_ground_truth": [max_ang, max_tr],
                       "mean_source_edge_points": mean_src},
