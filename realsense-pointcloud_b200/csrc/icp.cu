@@ -1013,8 +1013,9 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   bool want_persist = false;
   {
     const char* env = getenv("RSPCL_ICP_PERSIST");
-    want_persist = !(env && env[0] == '0') && !sharded && !brute && tgt->max_count_hint <= P_NTMAX &&
-                   src->max_count_hint > 0 && src->max_count_hint < 65536;
+    // (a target above the shared-memory capacity only sends ITS pair to the global-memory path, see below)
+    want_persist = !(env && env[0] == '0') && !sharded && !brute && src->max_count_hint > 0 && src->max_count_hint < 65536 &&
+                   (S > 1 || tgt->max_count_hint <= P_NTMAX);
   }
   if (want_persist) {
     k_copy_work<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, work, wstride);
@@ -1026,6 +1027,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
 
   // ---- persistent shared-memory path: one cluster per pair, all iterations in one launch (icp_persist.cuh)
   bool persist_done = false;
+  int active_init = S;  // pairs the global-memory path still has to run
   double* totals = nullptr;
   if (sharded) CU(ctx, scratch_alloc(ctx, &totals, (size_t)S * NRED));
   {
@@ -1055,6 +1057,8 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         }
       }
       int* d_order = nullptr;
+      unsigned short* d_tidx = nullptr;  // original index of every cell-sorted target point (tie-breaks, first_corr)
+      CU(ctx, scratch_alloc(ctx, &d_tidx, (size_t)S * 4 * P_NTMAX));  // one replica per CTA of a cluster (<= 4)
       float* d_lb = nullptr;  // per-point certified lower bound of the distance to every non-cached target point
       CU(ctx, scratch_alloc(ctx, &d_lb, (size_t)S * wstride));
       CU(ctx, cudaMemsetAsync(d_lb, 0, (size_t)S * wstride * sizeof(float), ctx->stream));
@@ -1093,11 +1097,11 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       ProfScope prof(ctx, "k_icp_persist", 0.0);
       cudaError_t le;
       if (cl == 4)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_dbg);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_dbg);
       else if (cl == 2)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_dbg);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_dbg);
       else
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_dbg);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_dbg);
       CU(ctx, le);
       LAUNCH_CHECK(ctx);
       prof.end();
@@ -1124,18 +1128,22 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       scratch_free(ctx, d_status);
       scratch_free(ctx, d_order);
       scratch_free(ctx, d_lb);
-      bool fallback = false;
+      scratch_free(ctx, d_tidx);
+      int n_failed = 0;
       double units = 0;
       for (int s = 0; s < S; ++s) {
-        if (hs[s]) fallback = true;
-        units += (double)hc[s] * (hst0[s].iterations > 0 ? hst0[s].iterations : 1);
+        if (hs[s]) ++n_failed;
+        else units += (double)hc[s] * (hst0[s].iterations > 0 ? hst0[s].iterations : 1);
       }
       prof.set_units(units);
-      if (!fallback) {
+      if (n_failed == 0) {
         persist_done = true;
-      } else {  // a target did not fit the shared-memory grid: redo the whole batch on the global-memory path
-        k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, S);
-        LAUNCH_CHECK(ctx);
+      } else {
+        // Some targets did not fit the shared-memory grid (too many points / occupied cells).  Those pairs left the kernel
+        // before touching their state, so they are still freshly initialised; the finished pairs carry done = 1 and are
+        // skipped by every kernel of the global-memory path, which now runs for the remaining ones only.
+        active_init = n_failed;
+        CU(ctx, small_h2d(ctx, n_active, &active_init, sizeof(int)));
         const int rcs = build_sorted_work();
         if (rcs) return rcs;
       }
@@ -1153,7 +1161,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   // iteration loop: launches are enqueued in growing chunks; the host only looks at the active-pair counter
   // between chunks (1, 1, 2, 4, 8, ... iterations), so the reference's one-iteration aligns cost one read-back.
   dim3 gstep(nblk, S);
-  int done_iters = 0, chunk = 1, active = persist_done ? 0 : S;
+  int done_iters = 0, chunk = 1, active = persist_done ? 0 : active_init;
   if (use_cache && !persist_done) {
     const size_t np = (size_t)S * wstride;
     CU(ctx, scratch_alloc(ctx, &g_lb, np));

@@ -3,7 +3,7 @@
 //
 // Why: edge clouds are ~10^4 points, so a per-iteration launch is bound by dependent L2 round trips and launch
 // latency, not by HBM (profiles/r01_v1_summary.md).  B200 gives 227 KB of shared memory per CTA: the whole
-// voxel-filtered target (<= 12288 points as SoA x/y/z + 16-bit original index = 168 KB) and its cell table (4096 x 8 B)
+// voxel-filtered target (<= 14336 points as SoA x/y/z = 168 KB; the 16-bit original indices stay in global memory) and its cell table (4096 x 8 B)
 // fit in one SM, so every neighbour-cell probe and candidate read becomes an LDS (~30 cycles) instead of an L2 access
 // (~300+ cycles), the convergence test never leaves the SM and the host never polls.
 //   * cluster of CL CTAs per pair (CL = 4, 2 or 1 chosen from the batch size so the chip is filled): every CTA holds
@@ -18,7 +18,7 @@
 // (icp.cu includes <cooperative_groups.h> and defines `cg` before entering its anonymous namespace)
 
 constexpr int P_THREADS = 512;
-constexpr int P_NTMAX = 12288;                 // target points resident per CTA
+constexpr int P_NTMAX = 14336;                 // target points resident per CTA
 constexpr int P_CAP = 4096;                    // cell-table slots (power of two)
 constexpr unsigned P_EMPTY = 0xFFFFFFFFu;
 constexpr int P_WARPS = P_THREADS / 32;
@@ -45,7 +45,6 @@ __device__ __forceinline__ void icp_accumulate(double* acc, float px, float py, 
 
 struct PersistSmem {
   float tx[P_NTMAX], ty[P_NTMAX], tz[P_NTMAX];
-  unsigned short tidx[P_NTMAX];
   uint2 tab[P_CAP];                 // {key, start << 16 | count}
   union {
     unsigned short fill[P_CAP];     // build-time cursors
@@ -73,7 +72,8 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstride, IcpState* __restrict__ st_g,
               const float4* __restrict__ tgt, const int* __restrict__ tcount, int tstride, int shared_target,
               IcpDevParams prm, float inv_cs, int* __restrict__ first_corr, int* __restrict__ status,
-              const int* __restrict__ order, float* __restrict__ lb, long long* __restrict__ dbg) {
+              const int* __restrict__ order, float* __restrict__ lb, unsigned short* __restrict__ tidx_g,
+              long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char p_smem_raw[];
   PersistSmem& S = *reinterpret_cast<PersistSmem*>(p_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -83,6 +83,10 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
   const int nt = tcount[tseg];
   const int ns = count[pair];
   const float4* T = tgt + (size_t)tseg * tstride;
+  // original target index of every cell-sorted point: only needed to break exact distance ties and to report the first
+  // correspondences, so it lives in global memory (one copy per CTA: the order inside a cell depends on each CTA's atomics) and the 2 B per
+  // point it would cost in shared memory buy 2048 more resident target points
+  unsigned short* TI = tidx_g + ((size_t)pair * CL + crank) * P_NTMAX;
 
   // ---------------------------------------------------------------- build the target replica in shared memory
   if (tid == 0) {
@@ -223,7 +227,32 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
     S.tx[pos] = p.x;
     S.ty[pos] = p.y;
     S.tz[pos] = p.z;
-    S.tidx[pos] = (unsigned short)i;
+    TI[pos] = (unsigned short)i;
+  }
+  __syncthreads();
+  // Order every cell by original index (insertion sort, cells hold a few dozen points at most): an ascending scan with
+  // a strict '<' then resolves exact distance ties inside a cell to the lowest original index without looking at TI,
+  // and the replica no longer depends on the order in which the atomics of pass B happened to land.
+  for (int sl = tid; sl < P_CAP; sl += P_THREADS) {
+    const uint2 e = S.tab[sl];
+    if (e.x == P_EMPTY) continue;
+    const int b = (int)(e.y >> 16), n = (int)(e.y & 0xFFFFu);
+    for (int a = b + 1; a < b + n; ++a) {
+      const unsigned short id = TI[a];
+      const float x = S.tx[a], y = S.ty[a], z = S.tz[a];
+      int c = a - 1;
+      while (c >= b && TI[c] > id) {
+        TI[c + 1] = TI[c];
+        S.tx[c + 1] = S.tx[c];
+        S.ty[c + 1] = S.ty[c];
+        S.tz[c + 1] = S.tz[c];
+        --c;
+      }
+      TI[c + 1] = id;
+      S.tx[c + 1] = x;
+      S.ty[c + 1] = y;
+      S.tz[c + 1] = z;
+    }
   }
   __syncthreads();
 
@@ -306,7 +335,7 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
             continue;
           }
           const bool ok = kp >= 0 && !((double)bd > prm.max_dist_sqr);
-          if (want_corr) first_corr[(size_t)pair * wstride + (int)(wbits & 0xFFFFu)] = ok ? (int)S.tidx[kp] : -1;
+          if (want_corr) first_corr[(size_t)pair * wstride + (int)(wbits & 0xFFFFu)] = ok ? (int)TI[kp] : -1;
           if (ok) icp_accumulate(acc, p.x, p.y, p.z, S.tx[kp], S.ty[kp], S.tz[kp], bd);
         }
       }
@@ -334,7 +363,7 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
             rr = fminf(rmax, s1 + slack);
           }
         }
-        int best = -1, kbest = 0;
+        int kbest = -1;
         float bd = INFINITY, d2nd = INFINITY;  // d2nd: smallest squared distance among scanned points other than the winner
         {
           const int x0 = p_cell(p.x - rr, inv_cs) - ox, x1 = p_cell(p.x + rr, inv_cs) - ox;
@@ -356,15 +385,10 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
 #pragma unroll 4
               for (int k = b; k < en; ++k) {
                 const float d = (k == kp) ? INFINITY : dist2_l2simple(p.x, p.y, p.z, S.tx[k], S.ty[k], S.tz[k]);
-                const int idx = (int)S.tidx[k];
-                if (d < bd || (d == bd && idx < best)) {
-                  d2nd = bd;
-                  bd = d;
-                  best = idx;
-                  kbest = k;
-                } else {
-                  d2nd = fminf(d2nd, d);
-                }
+                const bool lt = d < bd;  // ascending original index inside the cell: strict '<' keeps the lowest on a tie
+                d2nd = lt ? bd : fminf(d2nd, d);
+                kbest = lt ? k : kbest;
+                bd = lt ? d : bd;
               }
             }
           }
@@ -372,22 +396,19 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {  // top-2 merge across the 8 cells (every lane ends with the group result)
           const float obd = __shfl_xor_sync(0xffffffffu, bd, o), o2 = __shfl_xor_sync(0xffffffffu, d2nd, o);
-          const int ob = __shfl_xor_sync(0xffffffffu, best, o), ok_ = __shfl_xor_sync(0xffffffffu, kbest, o);
-          if (obd < bd || (obd == bd && ob < best)) {
+          const int ok_ = __shfl_xor_sync(0xffffffffu, kbest, o);
+          if (obd < bd || (obd == bd && ok_ >= 0 && kbest >= 0 && TI[ok_] < TI[kbest])) {
             d2nd = fminf(o2, bd);
             bd = obd;
-            best = ob;
             kbest = ok_;
           } else {
             d2nd = fminf(d2nd, obd);
           }
         }
         if (kp >= 0) {  // merge the cached incumbent (skipped by the scan)
-          const int bc = (int)S.tidx[kp];
-          if (bdc < bd || (bdc == bd && bc < best)) {
+          if (bdc < bd || (bdc == bd && kbest >= 0 && TI[kp] < TI[kbest])) {
             d2nd = bd;
             bd = bdc;
-            best = bc;
             kbest = kp;
           } else {
             d2nd = fminf(d2nd, bdc);
@@ -397,9 +418,9 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
           // points outside the scanned cells are farther than rr minus the rounding of the cell-boundary test
           const float edge = rr - 2e-7f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + rr);
           LB[i] = fminf(sqrt_approx(d2nd), edge) * 0.9999f;
-          W[i].w = __uint_as_float(((unsigned)(best >= 0 ? kbest + 1 : 0) << 16) | (unsigned)orig);
-          const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
-          if (want_corr) first_corr[(size_t)pair * wstride + orig] = ok ? best : -1;
+          W[i].w = __uint_as_float(((unsigned)(kbest + 1) << 16) | (unsigned)orig);
+          const bool ok = kbest >= 0 && !((double)bd > prm.max_dist_sqr);
+          if (want_corr) first_corr[(size_t)pair * wstride + orig] = ok ? (int)TI[kbest] : -1;
           if (ok) icp_accumulate(acc, p.x, p.y, p.z, S.tx[kbest], S.ty[kbest], S.tz[kbest], bd);
         }
       }

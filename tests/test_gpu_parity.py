@@ -402,7 +402,7 @@ def test_frames_with_holes_and_nans(ctx, pair2):
 # ------------------------------------------------------------------ global-memory ICP path (certified-cache passes)
 @pytest.fixture
 def global_path(monkeypatch):
-    """Force icp_align off the shared-memory persistent kernel (what clouds > 12288 target points take anyway)."""
+    """Force icp_align off the shared-memory persistent kernel (what clouds > 14336 target points take anyway)."""
     monkeypatch.setenv("RSPCL_ICP_PERSIST", "0")
     yield monkeypatch
 
@@ -457,7 +457,7 @@ def test_icp_global_path_batch_mixed_states(ctx, global_path):
 
 
 def test_icp_large_target_takes_global_path(ctx):
-    """A target above the shared-memory capacity (12288 points) goes to the grid path without any env override."""
+    """A target above the shared-memory capacity (14336 points) goes to the grid path without any env override."""
     rng = np.random.default_rng(31)
     tgt = rand_cloud(rng, 40000, 0.5)
     T = rigid(rng, 0.002, 0.002)
@@ -472,3 +472,28 @@ def test_icp_large_target_takes_global_path(ctx):
     assert ang < 1e-4 and tr < 1e-4
     ang, tr = pose_err(res[0]["T"], T)
     assert ang < 1e-3 and tr < 1e-3
+
+
+def test_icp_batch_mixing_shared_memory_and_global_pairs(ctx):
+    """One pair of the batch exceeds the shared-memory capacity: only that pair takes the global-memory path, the others
+    keep the persistent kernel's result (a whole-batch fallback used to make an entire sweep 3x slower)."""
+    rng = np.random.default_rng(37)
+    srcs, tgts = [], []
+    for k, nt in enumerate((4000, 20000, 3000)):
+        t = rand_cloud(rng, nt, 0.5)
+        T = rigid(rng, 0.002, 0.002)
+        srcs.append(orc.transform(t[::3], np.linalg.inv(T)))
+        tgts.append(t)
+    kw = dict(max_iterations=12, max_corr_dist=0.02, transformation_epsilon=-1.0, euclidean_fitness_epsilon=-1e300,
+              mse_threshold_absolute=-1.0)
+    res, aligned, fc = R.icp_align(ctx, ctx.upload(srcs), ctx.upload(tgts), R.icp_params(**kw), want_first_corr=True)
+    al = aligned.download()
+    off = 0
+    for k in range(3):
+        o = orc.icp_align(srcs[k], tgts[k], orc.icp_params(**kw), want_first_corr=True)
+        assert np.array_equal(fc[off:off + len(srcs[k])], o["first_corr"]), k
+        off += len(srcs[k])
+        assert res[k]["iterations"] == 12 and res[k]["n_corr"] == o["n_corr"], k
+        ang, tr = pose_err(res[k]["T"], o["T"])
+        assert ang < 1e-4 and tr < 1e-4, (k, ang, tr)
+        assert np.array_equal(al[k].view(np.uint32), orc.transform(srcs[k], res[k]["T"]).view(np.uint32))
