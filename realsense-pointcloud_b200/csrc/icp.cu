@@ -1116,11 +1116,11 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         std::vector<long long> hd((size_t)S * cl * 8);
         CU(ctx, cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "persist dbg: S=%d cl=%d  [pair crank ns iters | phaseA rescans(k) phaseB reduce+exchange solve head | total] kcycles\n", S, cl);
+        fprintf(stderr, "persist dbg: S=%d cl=%d  [pair crank ns rescans iters | phaseA waitA phaseB reduce+exchange solve head | total] kcycles\n", S, cl);
         for (int s = 0; s < S; ++s)
           for (int c = 0; c < cl; ++c) {
             const long long* D = &hd[((size_t)s * cl + c) * 8];
-            fprintf(stderr, "  %3d %d %6lld %3d | %7.1f %7.1f %7.1f %7.1f %7.1f %7.1f | %8.1f\n", s, c, D[6], hst0[s].iterations, D[0] / 1e3,
+            fprintf(stderr, "  %3d %d %6d %6lld %3d | %7.1f %7.1f %7.1f %7.1f %7.1f %7.1f | %8.1f\n", s, c, hc[s], D[6], hst0[s].iterations, D[0] / 1e3,
                     D[1] / 1e3, D[2] / 1e3, D[3] / 1e3, D[4] / 1e3, D[5] / 1e3, D[7] / 1e3);
           }
         scratch_free(ctx, d_dbg);

@@ -22,6 +22,7 @@ constexpr int P_NTMAX = 14336;                 // target points resident per CTA
 constexpr int P_CAP = 4096;                    // cell-table slots (power of two)
 constexpr unsigned P_EMPTY = 0xFFFFFFFFu;
 constexpr int P_WARPS = P_THREADS / 32;
+constexpr int P_G = 4;                         // lanes that share one re-query (phase B)
 constexpr int P_WL = 7168;                     // work-list entries (points per phase-A/B round)
 
 // MUFU.SQRT (2^-22 relative error): only used for bounds that carry a 1e-5 safety margin
@@ -264,7 +265,7 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
   const float slack = 0.5f * r;
   const int span = S.cmax[0] - ox, spany = S.cmax[1] - oy, spanz = S.cmax[2] - oz;
   int parity = 0;
-  long long tph[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();  // debug phase timers (thread 0; only stored if dbg != nullptr)
+  long long tph[6] = {0, 0, 0, 0, 0, 0}, tc = clock64(), n_rescan = 0;  // debug phase timers (thread 0; only stored if dbg != nullptr)
 #define P_TICK(k) do { if (dbg && tid == 0) { const long long n_ = clock64(); tph[k] += n_ - tc; tc = n_; } } while (0)
   if (dbg && tid == 0) dbg[((size_t)pair * CL + crank) * 8 + 6] = tc;
   while (true) {
@@ -341,11 +342,12 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
       }
       P_TICK(0);
       __syncthreads();
-      if (dbg && tid == 0) tph[1] += S.nwork;  // debug: rescans
-      // ---------------- phase B: 8 lanes per work item, one neighbour cell each, merged with xor shuffles
+      P_TICK(1);
+      if (dbg && tid == 0) n_rescan += S.nwork;
+      // ---------------- phase B: P_G lanes per work item (each probes 8 / P_G neighbour cells), top-2 merged with xor shuffles
       const int nwork = S.nwork;
-      for (int jb = wid * 4; jb < nwork; jb += P_WARPS * 4) {  // warp-uniform trip count (full-mask shuffles below)
-        const int j = jb + (lane >> 3), c = lane & 7;
+      for (int jb = wid * (32 / P_G); jb < nwork; jb += P_WARPS * (32 / P_G)) {  // warp-uniform trip count (full-mask shuffles)
+        const int j = jb + lane / P_G, c = lane % P_G;
         const bool active = j < nwork;
         const int i = base + (active ? (int)S.wl[j] : 0);
         const float4 p = W[i];  // already transformed by phase A
@@ -365,36 +367,55 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
         }
         int kbest = -1;
         float bd = INFINITY, d2nd = INFINITY;  // d2nd: smallest squared distance among scanned points other than the winner
+        unsigned cell[8 / P_G];                // this lane's neighbour cells: start << 16 | count (0: empty / duplicate / outside)
         {
           const int x0 = p_cell(p.x - rr, inv_cs) - ox, x1 = p_cell(p.x + rr, inv_cs) - ox;
           const int y0 = p_cell(p.y - rr, inv_cs) - oy, y1 = p_cell(p.y + rr, inv_cs) - oy;
           const int z0 = p_cell(p.z - rr, inv_cs) - oz, z1 = p_cell(p.z + rr, inv_cs) - oz;
-          const bool dup = ((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0);
-          const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
-          const bool inside = (unsigned)ix <= (unsigned)span && (unsigned)iy <= (unsigned)spany && (unsigned)iz <= (unsigned)spanz;
-          if (active && !dup && inside) {
-            const unsigned key = ((unsigned)ix << 20) | ((unsigned)iy << 10) | (unsigned)iz;
-            unsigned s = p_hash(key);
-            uint2 e = S.tab[s];
-            while (e.x != key && e.x != P_EMPTY) {
-              s = (s + 1) & (P_CAP - 1);
-              e = S.tab[s];
-            }
-            if (e.x == key) {
-              const int b = (int)(e.y >> 16), en = b + (int)(e.y & 0xFFFFu);
-#pragma unroll 4
-              for (int k = b; k < en; ++k) {
-                const float d = (k == kp) ? INFINITY : dist2_l2simple(p.x, p.y, p.z, S.tx[k], S.ty[k], S.tz[k]);
-                const bool lt = d < bd;  // ascending original index inside the cell: strict '<' keeps the lowest on a tie
-                d2nd = lt ? bd : fminf(d2nd, d);
-                kbest = lt ? k : kbest;
-                bd = lt ? d : bd;
+#pragma unroll
+          for (int q = 0; q < 8 / P_G; ++q) {
+            const int cc = c + q * P_G;
+            cell[q] = 0u;
+            const bool dup = ((cc & 1) && x1 == x0) || ((cc & 2) && y1 == y0) || ((cc & 4) && z1 == z0);
+            const int ix = (cc & 1) ? x1 : x0, iy = (cc & 2) ? y1 : y0, iz = (cc & 4) ? z1 : z0;
+            const bool inside = (unsigned)ix <= (unsigned)span && (unsigned)iy <= (unsigned)spany && (unsigned)iz <= (unsigned)spanz;
+            if (active && !dup && inside) {
+              const unsigned key = ((unsigned)ix << 20) | ((unsigned)iy << 10) | (unsigned)iz;
+              unsigned s = p_hash(key);
+              uint2 e = S.tab[s];
+              while (e.x != key && e.x != P_EMPTY) {
+                s = (s + 1) & (P_CAP - 1);
+                e = S.tab[s];
               }
+              if (e.x == key) cell[q] = e.y;
+            }
+          }
+        }
+        // The lanes of the group now walk the (<= 8) occupied cells together, lane `c` taking every P_G-th candidate:
+        // consecutive lanes read consecutive shared-memory words (no bank conflicts inside a group) and the work is
+        // balanced however unevenly the points are spread over the cells.
+#pragma unroll
+        for (int q = 0; q < 8 / P_G; ++q) {
+#pragma unroll 1
+          for (int sl = 0; sl < P_G; ++sl) {
+            const unsigned ey = __shfl_sync(0xffffffffu, cell[q], sl, P_G);
+            const int b = (int)(ey >> 16), en = b + (int)(ey & 0xFFFFu);
+            for (int k = b + c; k < en; k += P_G) {
+              const float d = (k == kp) ? INFINITY : dist2_l2simple(p.x, p.y, p.z, S.tx[k], S.ty[k], S.tz[k]);
+              if (d == bd && d < INFINITY) {  // exact tie (rare): the lowest original index wins
+                if (TI[k] < TI[kbest]) kbest = k;
+                d2nd = bd;
+                continue;
+              }
+              const bool lt = d < bd;
+              d2nd = lt ? bd : fminf(d2nd, d);
+              kbest = lt ? k : kbest;
+              bd = lt ? d : bd;
             }
           }
         }
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {  // top-2 merge across the 8 cells (every lane ends with the group result)
+        for (int o = 1; o < P_G; o <<= 1) {  // top-2 merge across the group (every lane ends with the group result)
           const float obd = __shfl_xor_sync(0xffffffffu, bd, o), o2 = __shfl_xor_sync(0xffffffffu, d2nd, o);
           const int ok_ = __shfl_xor_sync(0xffffffffu, kbest, o);
           if (obd < bd || (obd == bd && ok_ >= 0 && kbest >= 0 && TI[ok_] < TI[kbest])) {
@@ -469,7 +490,7 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
     long long* D = dbg + ((size_t)pair * CL + crank) * 8;
     for (int k = 0; k < 6; ++k) D[k] = tph[k];
     D[7] = clock64() - D[6];
-    D[6] = ns;
+    D[6] = n_rescan;
   }
 #undef P_TICK
 }
