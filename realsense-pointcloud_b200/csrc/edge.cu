@@ -9,8 +9,9 @@
 //   K1  k_canny_nms   gray -> 3x3 Gaussian (9-tap, clamp) -> Sobel (clamp) -> sqrtf magnitude -> direction bin
 //                     -> non-maximum suppression, fused over a shared-memory halo tile; writes a 1-byte class
 //                     (0 none, 1 weak >= t_low, 2 strong >= t_high) and seeds the union-find parents.
-//   K1b k_uf_merge / k_uf_flag / k_edge_mask   hysteresis as 8-connected components of {class>0} that contain a
-//                     strong pixel (lock-free union-find; the result is order-independent, so it is exact).
+//   K1b (in k_canny_nms) + k_uf_border / k_uf_flag / k_edge_mask   hysteresis as 8-connected components of {class>0}
+//                     that contain a strong pixel: lock-free union-find, tile-local in shared memory inside K1, stitched
+//                     across tile borders in global memory (the result is order-independent, so it is exact).
 //   K1c k_block_count / k_seg_scan / k_scatter  mask -> ascending row-major compaction (copyPointCloud(indices)).
 // Roofline: HBM-bound; algorithmic bytes per pixel = 1 R (gray) + 1 W (class) for K1.
 #include "common.cuh"
@@ -43,11 +44,40 @@ __device__ __forceinline__ int direction_bin(float gy, float gx) {
   return 255;
 }
 
+// ---- lock-free union-find over candidate pixels (per frame; parents are pixel indices within the frame)
+__device__ __forceinline__ int uf_find(volatile int* parent, int x) {
+  int p = parent[x];
+  while (p != x) {
+    int gp = parent[p];
+    if (gp != p) parent[x] = gp;  // path halving: gp is an ancestor, benign under concurrency
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      int t = a;
+      a = b;
+      b = t;
+    }
+    int old = atomicCAS(&parent[a], a, b);  // link the larger root under the smaller
+    if (old == a) return;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ gray, int w, int h, int stride, float t_low,
                                                    float t_high, uint8_t* __restrict__ cls, int* __restrict__ parent) {
   __shared__ float s_gray[GH][GW + 1];
   __shared__ float s_blur[BH][BW + 1];
   __shared__ float s_mag[MH][MW + 1];
+  __shared__ uint8_t s_cls[TH][TW];
+  __shared__ int s_par[TH * TW];  // tile-local union-find (parents are local pixel indices i * TW + j)
   const int seg = blockIdx.z;
   const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -145,54 +175,69 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
         if (ok && m >= a && m >= b) out = (m >= t_high) ? 2 : 1;
       }
     }
-    const size_t gidx = (size_t)seg * stride + (size_t)r * w + c;
-    cls[gidx] = out;
-    if (out) parent[gidx] = r * w + c;
+    s_cls[i][j] = out;
+    cls[(size_t)seg * stride + (size_t)r * w + c] = out;
   }
-}
-
-// ---- lock-free union-find over candidate pixels (per frame; parents are pixel indices within the frame)
-__device__ __forceinline__ int uf_find(volatile int* parent, int x) {
-  int p = parent[x];
-  while (p != x) {
-    int gp = parent[p];
-    if (gp != p) parent[x] = gp;  // path halving: gp is an ancestor, benign under concurrency
-    x = p;
-    p = gp;
+  // 5. hysteresis, tile-local part: 8-connected components of the candidates inside this tile are merged in shared
+  //    memory; every candidate then points straight at its tile root (the smallest pixel index of its local component,
+  //    the same "larger under smaller" rule as the global merge), so k_uf_border only has to stitch tile borders.
+  for (int k = tid; k < TH * TW; k += 256) {
+    const int i = k / TW, j = k % TW;
+    s_par[k] = k;
+    if (r0 + i >= h || c0 + j >= w) s_cls[i][j] = 0;
   }
-  return x;
-}
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
-  while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) {
-      int t = a;
-      a = b;
-      b = t;
+  __syncthreads();
+  for (int k = tid; k < TH * TW; k += 256) {
+    const int i = k / TW, j = k % TW;
+    if (!s_cls[i][j]) continue;
+    if (j > 0 && s_cls[i][j - 1]) uf_union(s_par, k, k - 1);
+    if (i > 0) {
+      if (j > 0 && s_cls[i - 1][j - 1]) uf_union(s_par, k, k - TW - 1);
+      if (s_cls[i - 1][j]) uf_union(s_par, k, k - TW);
+      if (j < TW - 1 && s_cls[i - 1][j + 1]) uf_union(s_par, k, k - TW + 1);
     }
-    int old = atomicCAS(&parent[a], a, b);  // link the larger root under the smaller
-    if (old == a) return;
+  }
+  __syncthreads();
+  for (int k = tid; k < TH * TW; k += 256) {
+    const int i = k / TW, j = k % TW;
+    if (!s_cls[i][j]) continue;
+    const int root = uf_find(s_par, k);
+    parent[(size_t)seg * stride + (size_t)(r0 + i) * w + (c0 + j)] = (r0 + root / TW) * w + (c0 + root % TW);
   }
 }
 
-__global__ void k_uf_merge(const uint8_t* __restrict__ cls, int* __restrict__ parent, int w, int h, int stride) {
+// stitch the tile-local components across tile borders (the only unions left): candidates in the first row, first column
+// or last column of a k_canny_nms tile are united with their backward neighbours in global memory
+__global__ void k_uf_border(const uint8_t* __restrict__ cls, int* __restrict__ parent, int w, int h, int stride) {
   const int seg = blockIdx.y;
   const uint8_t* c = cls + (size_t)seg * stride;
   int* par = parent + (size_t)seg * stride;
-  const int n = w * h;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (!c[i]) continue;
-    const int r = i / w, col = i % w;
-    // candidates are interior pixels, so the four backward neighbours are always in the image
-    if (c[i - 1]) uf_union(par, i, i - 1);
-    if (c[i - w - 1]) uf_union(par, i, i - w - 1);
-    if (c[i - w]) uf_union(par, i, i - w);
-    if (c[i - w + 1]) uf_union(par, i, i - w + 1);
-    (void)r;
-    (void)col;
+  // border pixels only: per tile row TW pixels of the top row + 2 (TH - 1) of the side columns
+  const int tiles_x = (w + TW - 1) / TW, tiles_y = (h + TH - 1) / TH;
+  constexpr int PER = TW + 2 * (TH - 1);
+  const long long total = (long long)tiles_x * tiles_y * PER;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(q / PER), e = (int)(q % PER);
+    const int ty = t / tiles_x, tx = t % tiles_x;
+    int i, j;
+    if (e < TW) {
+      i = 0;
+      j = e;
+    } else {
+      const int f = e - TW;
+      i = 1 + (f >> 1);
+      j = (f & 1) ? TW - 1 : 0;
+    }
+    const int r = ty * TH + i, col = tx * TW + j;
+    if (r >= h || col >= w) continue;
+    const int p = r * w + col;
+    if (!c[p]) continue;
+    // candidates are interior pixels, so the four backward neighbours are always in the image; unions with neighbours of
+    // the same tile are no-ops (already merged locally)
+    if (c[p - 1]) uf_union(par, p, p - 1);
+    if (c[p - w - 1]) uf_union(par, p, p - w - 1);
+    if (c[p - w]) uf_union(par, p, p - w);
+    if (c[p - w + 1]) uf_union(par, p, p - w + 1);
   }
 }
 
@@ -331,7 +376,7 @@ extern "C" int rspcl_edge_extract(rspcl_ctx* ctx, const rspcl_cloud* frames, flo
   }
   dim3 g2(blocks_per_seg(ctx, S, n, 256), S);
   ProfScope prof_h(ctx, "edge_hysteresis_compact", (double)S * n);
-  k_uf_merge<<<g2, 256, 0, ctx->stream>>>(cls, parent, w, h, stride);
+  k_uf_border<<<g2, 256, 0, ctx->stream>>>(cls, parent, w, h, stride);
   LAUNCH_CHECK(ctx);
   k_uf_flag<<<g2, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);
   LAUNCH_CHECK(ctx);
