@@ -441,7 +441,7 @@ def main():
                         "is ~2 % of the algorithmic bytes; the kernel is bound by the serial chain of one ICP iteration (stream, "
                         "re-query, reduce, cluster exchange, solve) on the slowest pair of the batch, not by HBM (SURVEY H3). "
                         "The HBM-bound regime (one 25 M-point pair, k_icp_stream: 4.5 TB/s of DRAM traffic, 27 % in algorithmic "
-                        "bytes) is in profiles/r01_v3_summary.md"}
+                        "bytes) is in profiles/r01_final_summary.md"}
 
     # ---- side measurement (rank 0, N=1): BASELINE configs[2], edge-based NDT on one 1280x720 pair, 0.05 m voxels
     ndt_leg = None
