@@ -125,6 +125,17 @@ cudaError_t small_h2d(rspcl_ctx* ctx, void* d_dst, const void* h_src, size_t byt
 cudaError_t small_d2h(rspcl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);  // valid after ctx_sync()
 cudaError_t ctx_sync(rspcl_ctx* ctx);
 int comm_allreduce_f64(rspcl_ctx* ctx, double* buf, size_t n);
+// ICP nearest-neighbour cache handed from one align to the next align of the same pairs (icp.cu; owned by the caller)
+struct IcpCarry {
+  float4* work = nullptr;          // final working cloud of the previous align (.w = cached slot + 1 << 16 | index)
+  float* lb = nullptr;             // certified bounds at those positions
+  unsigned short* tslot = nullptr; // original target index behind every cached slot
+  const float4* tgt_pts = nullptr; // the target the cache refers to
+  double max_corr_dist = 0;
+  int S = 0, wstride = 0;
+  bool valid = false;
+};
+void icp_carry_free(rspcl_ctx* ctx, IcpCarry* c);
 int blocks_per_seg(const rspcl_ctx* ctx, int n_seg, int max_count, int threads);
 int transform_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float* d_T, int broadcast, rspcl_cloud* out);
 int ensure_gray(rspcl_ctx* ctx, rspcl_cloud* c);

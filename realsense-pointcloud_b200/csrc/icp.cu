@@ -646,6 +646,31 @@ __global__ void k_pack_i32(const int* __restrict__ v, const int* __restrict__ co
 
 #include "icp_persist.cuh"
 
+// Working cloud of an align that continues a previous align of the same pairs (coarse -> fine, same source points moved
+// by the coarse result, same target): the new positions with the previous cache word (.w = slot + 1 << 16 | index) and
+// the previous bound lowered by the distance between the two positions of the point.
+__global__ void k_copy_work_carry(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
+                                  const float4* __restrict__ prev_work, const float* __restrict__ prev_lb,
+                                  float4* __restrict__ work, float* __restrict__ lb, int stride_work) {
+  const int seg = blockIdx.y;
+  const int n = count[seg];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = src[(size_t)seg * stride_src + i];
+    const float4 q = prev_work[(size_t)seg * stride_work + i];
+    float b = 0.f;
+    unsigned w = (unsigned)i;
+    if (finite3(p.x, p.y, p.z) && finite3(q.x, q.y, q.z)) {
+      b = prev_lb[(size_t)seg * stride_work + i] -
+          __fmaf_rn(sqrt_approx(dist2_l2simple(p.x, p.y, p.z, q.x, q.y, q.z)), 1.00001f, 1e-9f);
+      w = __float_as_uint(q.w);
+    }
+    p.w = __uint_as_float(w);
+    work[(size_t)seg * stride_work + i] = p;
+    lb[(size_t)seg * stride_work + i] = b;
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------------------------
 // Certified-cache correspondence passes for clouds that do not fit the shared-memory kernel (global-memory grid).
 // Per source point: ci = position of its cached match inside g.sorted (-1: none), lb = lower bound of the true distance
@@ -931,8 +956,16 @@ extern "C" void rspcl_icp_reference_params(rspcl_icp_params* p) {
 int radix_sort_pairs(rspcl_ctx* ctx, unsigned long long* keys, int* vals, unsigned long long* tmp_keys, int* tmp_vals,
                      long long n);
 
+void icp_carry_free(rspcl_ctx* ctx, IcpCarry* c) {
+  scratch_free(ctx, c->work);
+  scratch_free(ctx, c->lb);
+  scratch_free(ctx, c->tslot);
+  *c = IcpCarry();
+}
+
 int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
-                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, int* d_first_corr) {
+                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, int* d_first_corr,
+                     IcpCarry* carry_out, const IcpCarry* carry_in) {
   const int S = src->n_seg;
   const int shared_target = (tgt->n_seg == 1 && S > 1) ? 1 : 0;
   if (!shared_target && tgt->n_seg != S) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "icp_align: src has %d segments, tgt %d", S, tgt->n_seg);
@@ -1061,7 +1094,19 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       CU(ctx, scratch_alloc(ctx, &d_tidx, (size_t)S * 4 * P_NTMAX));  // one replica per CTA of a cluster (<= 4)
       float* d_lb = nullptr;  // per-point certified lower bound of the distance to every non-cached target point
       CU(ctx, scratch_alloc(ctx, &d_lb, (size_t)S * wstride));
-      CU(ctx, cudaMemsetAsync(d_lb, 0, (size_t)S * wstride * sizeof(float), ctx->stream));
+      // continue the cache of a previous align of the same pairs against the same target (coarse -> fine)?
+      const bool use_carry = carry_in && carry_in->valid && carry_in->S == S && carry_in->wstride == wstride &&
+                             carry_in->tgt_pts == tgt->pts && carry_in->max_corr_dist == prm->max_corr_dist && !d_first_corr;
+      unsigned short* d_ct = nullptr;  // target point behind every cached slot, for the next align (carry_out)
+      if (carry_out) CU(ctx, scratch_alloc(ctx, &d_ct, (size_t)S * wstride));
+      if (use_carry) {
+        k_copy_work_carry<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, carry_in->work, carry_in->lb,
+                                                          work, d_lb, wstride);
+        LAUNCH_CHECK(ctx);
+      } else {
+        CU(ctx, cudaMemsetAsync(d_lb, 0, (size_t)S * wstride * sizeof(float), ctx->stream));
+      }
+      const unsigned short* d_ci = use_carry ? carry_in->tslot : nullptr;
       CU(ctx, scratch_alloc(ctx, &d_order, (size_t)S));
       CU(ctx, small_h2d(ctx, d_order, order.data(), (size_t)S * sizeof(int)));
       const float inv_cs_p = 1.0f / (float)(prm->max_corr_dist * 4.1);
@@ -1071,13 +1116,10 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         CU(ctx, scratch_alloc(ctx, &d_dbg, (size_t)S * 4 * 8));
         CU(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)S * 4 * 8 * sizeof(long long), ctx->stream));
       }
-      static bool attr_set = false;
-      if (!attr_set) {
-        CU(ctx, cudaFuncSetAttribute(k_icp_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
-        CU(ctx, cudaFuncSetAttribute(k_icp_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
-        CU(ctx, cudaFuncSetAttribute(k_icp_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
-        attr_set = true;
-      }
+      // (per device and cheap: set on every call rather than caching a per-process flag)
+      CU(ctx, cudaFuncSetAttribute(k_icp_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
+      CU(ctx, cudaFuncSetAttribute(k_icp_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
+      CU(ctx, cudaFuncSetAttribute(k_icp_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(cl * S));
       cfg.blockDim = dim3(P_THREADS);
@@ -1097,11 +1139,11 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       ProfScope prof(ctx, "k_icp_persist", 0.0);
       cudaError_t le;
       if (cl == 4)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_dbg);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_ci, d_ct, d_dbg);
       else if (cl == 2)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_dbg);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_ci, d_ct, d_dbg);
       else
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_dbg);
+        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_ci, d_ct, d_dbg);
       CU(ctx, le);
       LAUNCH_CHECK(ctx);
       prof.end();
@@ -1127,9 +1169,24 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       }
       scratch_free(ctx, d_status);
       scratch_free(ctx, d_order);
-      scratch_free(ctx, d_lb);
       scratch_free(ctx, d_tidx);
       int n_failed = 0;
+      for (int s = 0; s < S; ++s) n_failed += hs[s] ? 1 : 0;
+      if (carry_out && n_failed == 0) {  // hand the working cloud, the bounds and the slot -> target map to the caller
+        carry_out->work = work;
+        carry_out->lb = d_lb;
+        carry_out->tslot = d_ct;
+        carry_out->S = S;
+        carry_out->wstride = wstride;
+        carry_out->tgt_pts = tgt->pts;
+        carry_out->max_corr_dist = prm->max_corr_dist;
+        carry_out->valid = true;
+        work = nullptr;
+      } else {
+        scratch_free(ctx, d_lb);
+        scratch_free(ctx, d_ct);
+      }
+      n_failed = 0;
       double units = 0;
       for (int s = 0; s < S; ++s) {
         if (hs[s]) ++n_failed;
@@ -1307,7 +1364,7 @@ extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rsp
     CU(ctx, small_h2d(ctx, d_guess, guess, (size_t)S * 16 * sizeof(float)));
   }
   if (first_corr) CU(ctx, scratch_alloc(ctx, &d_fc, (size_t)S * (src->stride ? src->stride : 1)));
-  rc = icp_align_device(ctx, src, tgt, prm, d_guess, results, aligned, d_fc);
+  rc = icp_align_device(ctx, src, tgt, prm, d_guess, results, aligned, d_fc, nullptr, nullptr);
   if (!rc && first_corr) {
     std::vector<int> off(S);
     long long total = 0;

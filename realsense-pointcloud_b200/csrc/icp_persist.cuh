@@ -74,6 +74,7 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
               const float4* __restrict__ tgt, const int* __restrict__ tcount, int tstride, int shared_target,
               IcpDevParams prm, float inv_cs, int* __restrict__ first_corr, int* __restrict__ status,
               const int* __restrict__ order, float* __restrict__ lb, unsigned short* __restrict__ tidx_g,
+              const unsigned short* __restrict__ carry_in, unsigned short* __restrict__ carry_out,
               long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char p_smem_raw[];
   PersistSmem& S = *reinterpret_cast<PersistSmem*>(p_smem_raw);
@@ -134,7 +135,31 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
   }
   __syncthreads();
   const int ox = S.origin[0], oy = S.origin[1], oz = S.origin[2];
-  // pass A: insert cells, count points per cell
+  // pass A1: insert the occupied cells with ORDERED linear probing (the smaller key keeps the slot, the larger one is
+  // carried on): the final table is the same whatever order the atomics land in, so the cell-sorted target -- and with it
+  // every cached slot number -- is reproducible from launch to launch (the fine align re-uses the coarse align's cache)
+  if (!S.flags[0]) {
+    for (int i = tid; i < nt; i += P_THREADS) {
+      const float4 p = T[i];
+      if (!finite3(p.x, p.y, p.z)) continue;
+      unsigned key = ((unsigned)(p_cell(p.x, inv_cs) - ox) << 20) | ((unsigned)(p_cell(p.y, inv_cs) - oy) << 10) |
+                     (unsigned)(p_cell(p.z, inv_cs) - oz);
+      unsigned s = p_hash(key);
+      int probes = 0;
+      while (true) {
+        const unsigned prev = atomicMin(&S.tab[s].x, key);  // P_EMPTY is the largest value
+        if (prev == P_EMPTY || prev == key) break;
+        if (prev > key) key = prev;  // displaced a larger key: it moves on
+        s = (s + 1) & (P_CAP - 1);
+        if (++probes >= P_CAP) {  // table full: this pair goes to the global-memory path
+          S.flags[0] = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // pass A2: count the points of every cell
   if (!S.flags[0]) {
     for (int i = tid; i < nt; i += P_THREADS) {
       const float4 p = T[i];
@@ -142,17 +167,8 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
       const unsigned key = ((unsigned)(p_cell(p.x, inv_cs) - ox) << 20) | ((unsigned)(p_cell(p.y, inv_cs) - oy) << 10) |
                            (unsigned)(p_cell(p.z, inv_cs) - oz);
       unsigned s = p_hash(key);
-      int probes = 0;
-      while (true) {
-        const unsigned prev = atomicCAS(&S.tab[s].x, P_EMPTY, key);
-        if (prev == P_EMPTY || prev == key) break;
-        s = (s + 1) & (P_CAP - 1);
-        if (++probes >= P_CAP) {  // table full: this pair goes to the global-memory path
-          S.flags[0] = 1;
-          break;
-        }
-      }
-      if (probes < P_CAP) atomicAdd(&S.tab[s].y, 1u);
+      while (S.tab[s].x != key) s = (s + 1) & (P_CAP - 1);
+      atomicAdd(&S.tab[s].y, 1u);
     }
   }
   __syncthreads();
@@ -264,6 +280,23 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
   const float rmax = __fdividef(0.485f, inv_cs);  // largest ball that touches <= 2 cells per axis (~1.99 x gate)
   const float slack = 0.5f * r;
   const int span = S.cmax[0] - ox, spany = S.cmax[1] - oy, spanz = S.cmax[2] - oz;
+  const int share = (ns + CL - 1) / CL;  // this CTA's contiguous slice [lo, hi) of the source
+  const int lo = crank * share, hi = min(ns, lo + share);
+  if (carry_in) {
+    // The working cloud arrives with the cache of a previous align of the same pair (coarse -> fine): a cached slot is
+    // only trusted if it still names the same target point in THIS launch's replica (original index carried alongside);
+    // anything else starts uncached.  The bounds were already lowered by the distance each point moved in between.
+    const unsigned short* CI = carry_in + (size_t)pair * wstride;
+    for (int i = lo + tid; i < hi; i += P_THREADS) {
+      const unsigned wb = __float_as_uint(W[i].w);
+      const int kp = (int)(wb >> 16) - 1;
+      if (kp >= 0 && (kp >= P_NTMAX || TI[kp] != CI[i])) {
+        W[i].w = __uint_as_float(wb & 0xFFFFu);
+        LB[i] = 0.f;
+      }
+    }
+    __syncthreads();
+  }
   int parity = 0;
   long long tph[6] = {0, 0, 0, 0, 0, 0}, tc = clock64(), n_rescan = 0;  // debug phase timers (thread 0; only stored if dbg != nullptr)
 #define P_TICK(k) do { if (dbg && tid == 0) { const long long n_ = clock64(); tph[k] += n_ - tc; tc = n_; } } while (0)
@@ -283,8 +316,6 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
     // unmatched: no cell is visited (phase A, straight-line code, two points in flight per thread).  The few points
     // whose bound no longer decides go to a shared-memory work list and are rescanned load-balanced over the whole CTA
     // (phase B, <= 2x2x2 cells), which also renews their bound.
-    const int share = (ns + CL - 1) / CL;           // this CTA's contiguous slice [lo, hi) of the (spatially sorted) source
-    const int lo = crank * share, hi = min(ns, lo + share);
     for (int base = lo; base < hi; base += P_WL) {  // one round unless the slice exceeds the work list
       const int end = min(hi, base + P_WL);
       if (tid == 0) S.nwork = 0;
@@ -483,6 +514,13 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
     P_TICK(4);
     __syncthreads();
     if (S.st.done) break;
+  }
+  if (carry_out) {  // what the next align of this pair needs to trust the cache: the target point behind every slot
+    unsigned short* CO = carry_out + (size_t)pair * wstride;
+    for (int i = lo + tid; i < hi; i += P_THREADS) {
+      const int kp = (int)(__float_as_uint(W[i].w) >> 16) - 1;
+      CO[i] = kp >= 0 ? TI[kp] : (unsigned short)0xFFFFu;
+    }
   }
   if (CL > 1) cg::this_cluster().sync();  // no CTA leaves while a sibling may still read its partials
   if (tid == 0 && crank == 0) st_g[pair] = S.st;

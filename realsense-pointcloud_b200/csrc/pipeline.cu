@@ -11,7 +11,8 @@
 #include <float.h>
 
 int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
-                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, int* d_first_corr);
+                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, int* d_first_corr,
+                     IcpCarry* carry_out, const IcpCarry* carry_in);
 int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_ndt_params* prm,
                      const float* d_guess, rspcl_ndt_result* h_results, rspcl_cloud* aligned);
 int voxel_approx_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float leaf[3], rspcl_cloud* out);
@@ -131,6 +132,9 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
   }
   std::vector<float> hT((size_t)n_pairs * 32);
   std::vector<rspcl_icp_result> fine(n_pairs);
+  // The fine align runs on the same pairs against the same targets, its source being the coarse source moved by the
+  // coarse result: it inherits the coarse align's certified nearest-neighbour cache instead of re-querying every point.
+  IcpCarry carry;
   if (coarse_kind == RSPCL_COARSE_NDT) {
     std::vector<rspcl_ndt_result> nr(n_pairs);
     rc = ndt_align_device(ctx, &Sc.c, &Tc.c, ndt, d_guess, nr.data(), &Ac.c);
@@ -142,8 +146,11 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
   } else {
     std::vector<rspcl_icp_result> cr(n_pairs);
     for (auto& r : cr) r.prev_mse = DBL_MAX;
-    rc = icp_align_device(ctx, &Sc.c, &Tc.c, icp, d_guess, cr.data(), &Ac.c, nullptr);
-    if (rc) return rc;
+    rc = icp_align_device(ctx, &Sc.c, &Tc.c, icp, d_guess, cr.data(), &Ac.c, nullptr, &carry, nullptr);
+    if (rc) {
+      icp_carry_free(ctx, &carry);
+      return rc;
+    }
     for (int i = 0; i < n_pairs; ++i) {
       memcpy(results[i].T_coarse, cr[i].T, 64);
       results[i].coarse_iterations = cr[i].iterations;
@@ -151,7 +158,8 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
   }
   // 5. fine ICP from identity on the coarse-aligned source
   for (auto& r : fine) r.prev_mse = DBL_MAX;
-  rc = icp_align_device(ctx, &Ac.c, &Tc.c, icp, nullptr, fine.data(), nullptr, nullptr);
+  rc = icp_align_device(ctx, &Ac.c, &Tc.c, icp, nullptr, fine.data(), nullptr, nullptr, nullptr, &carry);
+  icp_carry_free(ctx, &carry);
   if (rc) return rc;
   std::vector<int> accept(n_pairs);
   for (int i = 0; i < n_pairs; ++i) {

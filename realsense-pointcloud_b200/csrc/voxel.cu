@@ -233,11 +233,8 @@ int voxel_approx_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float leaf[
   if (out->n_seg != in->n_seg) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "voxel_approx: n_seg mismatch");
   const int S = in->n_seg;
   const float3 inv = make_float3(1.0f / leaf[0], 1.0f / leaf[1], 1.0f / leaf[2]);  // PCL: inverse_leaf_size_ in float
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(ctx, cudaFuncSetAttribute(k_approx_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOX_SMEM));
-    attr_set = true;
-  }
+  // per device and cheap: set on every call rather than caching a per-process flag (several devices per process)
+  CU(ctx, cudaFuncSetAttribute(k_approx_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOX_SMEM));
   const size_t tot = (size_t)S * (in->stride ? in->stride : 1);
   int *sorted = nullptr, *ev = nullptr, *d_over = nullptr;
   float4* tmp = nullptr;
