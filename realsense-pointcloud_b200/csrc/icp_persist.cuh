@@ -247,13 +247,17 @@ k_icp_persist(float4* __restrict__ work, const int* __restrict__ count, int wstr
     TI[pos] = (unsigned short)i;
   }
   __syncthreads();
-  // Order every cell by original index (insertion sort, cells hold a few dozen points at most): an ascending scan with
-  // a strict '<' then resolves exact distance ties inside a cell to the lowest original index without looking at TI,
-  // and the replica no longer depends on the order in which the atomics of pass B happened to land.
+  // Order every cell by original index (insertion sort, cells hold a few dozen points at most) so that the replica no
+  // longer depends on the order in which the atomics of pass B happened to land: slot numbers then mean the same target
+  // point in the next launch for the same target (cache carried from the coarse to the fine align).
   for (int sl = tid; sl < P_CAP; sl += P_THREADS) {
     const uint2 e = S.tab[sl];
     if (e.x == P_EMPTY) continue;
     const int b = (int)(e.y >> 16), n = (int)(e.y & 0xFFFFu);
+    // (a cell with hundreds of points -- a gate of the size of the scene -- is left as it landed: one thread sorting it
+    // would take O(n^2) global round trips; ties are still resolved by TI and carried slots are validated, so only the
+    // reproducibility of those slot numbers is given up)
+    if (n > 48) continue;
     for (int a = b + 1; a < b + n; ++a) {
       const unsigned short id = TI[a];
       const float x = S.tx[a], y = S.ty[a], z = S.tz[a];

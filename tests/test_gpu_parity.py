@@ -497,3 +497,20 @@ def test_icp_batch_mixing_shared_memory_and_global_pairs(ctx):
         ang, tr = pose_err(res[k]["T"], o["T"])
         assert ang < 1e-4 and tr < 1e-4, (k, ang, tr)
         assert np.array_equal(al[k].view(np.uint32), orc.transform(srcs[k], res[k]["T"]).view(np.uint32))
+
+
+def test_icp_gate_as_large_as_the_scene(ctx):
+    """A gate of the size of the cloud puts every target point into a handful of cells (degenerate for the shared-memory
+    grid: thousands of candidates per cell); results must still match the oracle and the call must not crawl."""
+    rng = np.random.default_rng(41)
+    tgt = rand_cloud(rng, 3000, 0.2)
+    T = rigid(rng, 0.02, 0.01)
+    src = orc.transform(tgt[::2], np.linalg.inv(T))
+    kw = dict(max_iterations=6, max_corr_dist=0.3, transformation_epsilon=-1.0, euclidean_fitness_epsilon=-1e300,
+              mse_threshold_absolute=-1.0)
+    res, _, fc = R.icp_align(ctx, ctx.upload([src]), ctx.upload([tgt]), R.icp_params(**kw), want_aligned=False, want_first_corr=True)
+    o = orc.icp_align(src, tgt, orc.icp_params(**kw), want_first_corr=True)
+    assert np.array_equal(fc, o["first_corr"])
+    assert res[0]["n_corr"] == o["n_corr"] == len(src)
+    ang, tr = pose_err(res[0]["T"], o["T"])
+    assert ang < 1e-4 and tr < 1e-4
