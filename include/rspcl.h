@@ -140,6 +140,14 @@ typedef struct rspcl_icp_result {
 int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
                     const float* guess, rspcl_icp_result* results, rspcl_cloud* aligned, int32_t* first_corr);
 
+/* Debug / parity variant of rspcl_icp_align: additionally returns the correspondences of the first n_dump_iterations
+ * iterations (pcl::registration::CorrespondenceEstimation::determineCorrespondences + the max-distance rejection, as
+ * IterativeClosestPoint::computeTransformation runs them every iteration: icp:95,104,111).  host_corr holds
+ * n_dump_iterations blocks, each packed like a download of src: index of the matched target point or -1.  Iterations the
+ * align did not execute (earlier convergence) read -1. */
+int rspcl_icp_align_dump(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
+                         const float* guess, rspcl_icp_result* results, int n_dump_iterations, int32_t* host_corr);
+
 /* pcl::Registration::getFitnessScore(max_range) on an already transformed source: mean squared NN distance over
  * the source points whose NN is within max_range (squared distance <= max_range), DBL_MAX if none. */
 int rspcl_fitness(rspcl_ctx* ctx, const rspcl_cloud* src_transformed, const rspcl_cloud* tgt, double max_range,

@@ -80,6 +80,9 @@ typedef struct OrcIcpResult {
  * receives the iteration-1 correspondence target index or -1. */
 void orc_icp_align(const OrcPoint* src, int ns, const OrcPoint* tgt, int nt, const OrcIcpParams* prm,
                    const float guess[16], OrcIcpResult* res, OrcPoint* aligned, int32_t* first_corr);
+/* the same align, returning the correspondences (target index or -1) of the first n_dump iterations: [n_dump][ns] */
+void orc_icp_align_dump(const OrcPoint* src, int ns, const OrcPoint* tgt, int nt, const OrcIcpParams* prm,
+                        const float guess[16], OrcIcpResult* res, int n_dump, int32_t* corr);
 /* Umeyama on explicit pairs (pcl::umeyama, with_scaling=false). use_float selects Scalar. */
 void orc_umeyama(const float* src_xyz, const float* tgt_xyz, int n, int use_float, float T[16]);
 /* Registration::getFitnessScore on an already transformed source */

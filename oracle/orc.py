@@ -196,6 +196,19 @@ def icp_align(src, tgt, prm, guess=None, prev_mse=None, want_aligned=True, want_
     return out
 
 
+def icp_align_dump(src, tgt, prm, guess=None, n_iters=1):
+    """Correspondences (target index or -1) of the first n_iters iterations: result dict, [n_iters, len(src)] int32."""
+    src, tgt = pts(src), pts(tgt)
+    res = IcpResult()
+    res.prev_mse = np.finfo(np.float64).max
+    g = mat_to_c(guess) if guess is not None else None
+    corr = np.zeros((n_iters, max(len(src), 1)), np.int32)
+    lib().orc_icp_align_dump(_p(src), len(src), _p(tgt), len(tgt), C.byref(prm), _p(g), C.byref(res), int(n_iters), _p(corr))
+    out = {"T": c_to_mat(res.T), "converged": bool(res.converged), "state": res.state, "iterations": res.iterations,
+           "n_corr": res.n_corr, "mse": res.mse, "prev_mse": res.prev_mse}
+    return out, corr[:, :len(src)]
+
+
 def umeyama(src_xyz, tgt_xyz, use_float=False):
     s = np.ascontiguousarray(src_xyz, np.float32)
     t = np.ascontiguousarray(tgt_xyz, np.float32)

@@ -169,10 +169,12 @@ extern "C" int orc_extract_edges(const OrcPoint* cloud, int w, int h, float t_lo
 }
 
 extern "C" int orc_crop35(const OrcPoint* cloud, int w, int h, OrcPoint* out, int* out_w, int* out_h) {
-  // blur_filter.hpp:23-35.  NOTE the loop bounds (h/5 .. h/5*4) can produce fewer rows than height*3/5
-  // when h % 5 != 0; the reference then leaves the tail of the resized vector default-constructed.
+  // blur_filter.hpp:23-35.  NOTE the loop bounds (h/5 .. h/5*4, w/5 .. w/5*4) can produce fewer points than
+  // (w*3/5)*(h*3/5) when w or h is not a multiple of 5 (e.g. RealSense 848x480: 507 copied columns, width 508).
+  // input_cloud->points.resize() SHRINKS the vector (blur_filter.hpp:25), so the tail [n_copied, ow*oh) keeps the
+  // points the input held at those indices before the call.
   int ow = w * 3 / 5, oh = h * 3 / 5;
-  for (int k = 0; k < ow * oh; ++k) out[k] = OrcPoint{0.f, 0.f, 0.f, 0xff000000u};  // default PointXYZRGB: a=255
+  for (int k = 0; k < ow * oh; ++k) out[k] = cloud[k];
   int i = 0;
   for (int r = h / 5; r < h / 5 * 4; r++)
     for (int c = w / 5; c < w / 5 * 4; c++) {

@@ -115,9 +115,10 @@ extern "C" void orc_umeyama(const float* src_xyz, const float* tgt_xyz, int n, i
     umeyama_impl<double>(src_xyz, tgt_xyz, n, T);
 }
 
-extern "C" void orc_icp_align(const OrcPoint* src, int ns, const OrcPoint* tgt, int nt, const OrcIcpParams* prm,
-                              const float guess[16], OrcIcpResult* res, OrcPoint* aligned, int32_t* first_corr) {
+static void icp_align_impl(const OrcPoint* src, int ns, const OrcPoint* tgt, int nt, const OrcIcpParams* prm,
+                           const float guess[16], OrcIcpResult* res, OrcPoint* aligned, int32_t* first_corr, int n_dump) {
   // Registration::align -> initCompute (kd-tree over target) -> computeTransformation
+  // first_corr: n_dump blocks of ns entries, block k = correspondences (target index or -1) of iteration k
   OrcKd* tree = orc_kd_build(tgt, nt);
   std::vector<OrcPoint> work(src, src + ns);  // input_transformed
   float final_T[16], T[16];
@@ -138,7 +139,7 @@ extern "C" void orc_icp_align(const OrcPoint* src, int ns, const OrcPoint* tgt, 
   double cur_mse = 0.0, last_mse = 0.0;
   std::vector<float> cs, ct, cd;
   if (first_corr)
-    for (int i = 0; i < ns; ++i) first_corr[i] = -1;
+    for (long long i = 0; i < (long long)ns * n_dump; ++i) first_corr[i] = -1;
 
   do {
     cs.clear();
@@ -150,7 +151,7 @@ extern "C" void orc_icp_align(const OrcPoint* src, int ns, const OrcPoint* tgt, 
       orc_kd_query(tree, &work[i], &j, &d);
       if (j < 0) continue;
       if (double(d) > max_dist_sqr) continue;
-      if (iterations == 0 && first_corr) first_corr[i] = j;
+      if (iterations < n_dump && first_corr) first_corr[(size_t)iterations * ns + i] = j;
       cs.push_back(work[i].x);
       cs.push_back(work[i].y);
       cs.push_back(work[i].z);
@@ -216,6 +217,16 @@ extern "C" void orc_icp_align(const OrcPoint* src, int ns, const OrcPoint* tgt, 
   res->prev_mse = prev_mse;
   if (aligned) orc_transform(src, ns, final_T, aligned);
   orc_kd_free(tree);
+}
+
+extern "C" void orc_icp_align(const OrcPoint* src, int ns, const OrcPoint* tgt, int nt, const OrcIcpParams* prm,
+                              const float guess[16], OrcIcpResult* res, OrcPoint* aligned, int32_t* first_corr) {
+  icp_align_impl(src, ns, tgt, nt, prm, guess, res, aligned, first_corr, 1);
+}
+
+extern "C" void orc_icp_align_dump(const OrcPoint* src, int ns, const OrcPoint* tgt, int nt, const OrcIcpParams* prm,
+                                   const float guess[16], OrcIcpResult* res, int n_dump, int32_t* corr) {
+  icp_align_impl(src, ns, tgt, nt, prm, guess, res, nullptr, corr, n_dump);
 }
 
 extern "C" double orc_fitness(const OrcPoint* src_transformed, int ns, const OrcPoint* tgt, int nt, double max_range) {

@@ -127,6 +127,11 @@ extern "C" void rspcl_ctx_destroy(rspcl_ctx* ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->z_host) cudaFreeHost(ctx->z_host);
+  for (int a = 0; a < RSPCL_AUX_STREAMS; ++a) {
+    if (ctx->aux[a]) cudaStreamDestroy(ctx->aux[a]);
+    if (ctx->ev_join[a]) cudaEventDestroy(ctx->ev_join[a]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -352,6 +357,7 @@ extern "C" int rspcl_cloud_upload(rspcl_ctx* ctx, rspcl_cloud* c, const void* ho
   c->height = height;
   c->max_count_hint = maxc;
   if (width * height > 0 && !c->gray) CU(ctx, cudaMalloc(&c->gray, (size_t)c->n_seg * c->stride));
+  c->gray_valid = false;
   const size_t esz = layout == RSPCL_LAYOUT_PCL32 ? 32 : 16;
   int* d_off = nullptr;
   void* raw = nullptr;
@@ -369,6 +375,7 @@ extern "C" int rspcl_cloud_upload(rspcl_ctx* ctx, rspcl_cloud* c, const void* ho
     else
       k_unpack<false><<<grid, 256, 0, ctx->stream>>>(raw, d_off, c->count, c->pts, c->gray, c->stride);
     LAUNCH_CHECK(ctx);
+    c->gray_valid = width * height > 0;  // the unpack kernel wrote the plane
   }
   scratch_free(ctx, d_off);
   scratch_free(ctx, (char*)raw);
@@ -453,10 +460,11 @@ int transform_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float* d_T, in
   k_transform<<<grid, 256, 0, ctx->stream>>>(in->pts, in->count, d_T, broadcast, out->pts, out == in ? nullptr : out->count,
                                              in->stride, out->stride);
   LAUNCH_CHECK(ctx);
-  if (out != in) {
+  if (out != in) {  // (in place the colours, hence the gray plane, are unchanged)
     out->max_count_hint = in->max_count_hint;
     out->width = in->width;
     out->height = in->height;
+    invalidate_gray(out);
   }
   return RSPCL_OK;
 }
@@ -510,6 +518,7 @@ extern "C" int rspcl_concat(rspcl_ctx* ctx, const rspcl_cloud* a, const rspcl_cl
   if (over) RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "concat: output stride %d too small", out->stride);
   out->max_count_hint = hint < out->stride ? hint : out->stride;
   out->width = out->height = 0;
+  invalidate_gray(out);
   return RSPCL_OK;
 }
 
@@ -530,6 +539,7 @@ extern "C" int rspcl_cloud_copy_segment(rspcl_ctx* ctx, const rspcl_cloud* src, 
                                                          dst->stride);
   LAUNCH_CHECK(ctx);
   if (src->max_count_hint > dst->max_count_hint) dst->max_count_hint = src->max_count_hint;
+  invalidate_gray(dst);  // a reused organized handle must not keep the previous frame's gray plane
   return RSPCL_OK;
 }
 
@@ -542,11 +552,11 @@ __global__ void k_crop35(const float4* __restrict__ in, float4* __restrict__ out
   const int cw = c1 - c0, n_src = (r1 - r0) * cw, n_out = ow * oh;
   if (blockIdx.x == 0 && threadIdx.x == 0) out_count[seg] = n_out;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
-    float4 p = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xff000000u));  // default-constructed PointXYZRGB tail
-    if (i < n_src) {
-      int r = r0 + i / cw, c = c0 + i % cw;
-      p = in[(size_t)seg * stride_in + (size_t)r * w + c];
-    }
+    // blur_filter.hpp:25 resizes by SHRINKING: entries the copy loop does not reach (w or h not a multiple of 5, e.g.
+    // 848x480) keep the input point of the same index
+    size_t from = (size_t)i;
+    if (i < n_src) from = (size_t)(r0 + i / cw) * w + (c0 + i % cw);
+    const float4 p = in[(size_t)seg * stride_in + from];
     out[(size_t)seg * stride_out + i] = p;
   }
 }
@@ -562,11 +572,12 @@ __global__ void k_gray_from_pts(const float4* __restrict__ pts, const int* __res
 }
 
 int ensure_gray(rspcl_ctx* ctx, rspcl_cloud* c) {
-  if (c->gray) return RSPCL_OK;
-  CU(ctx, cudaMalloc(&c->gray, (size_t)c->n_seg * (c->stride ? c->stride : 1)));
+  if (c->gray && c->gray_valid) return RSPCL_OK;
+  if (!c->gray) CU(ctx, cudaMalloc(&c->gray, (size_t)c->n_seg * (c->stride ? c->stride : 1)));
   dim3 grid(blocks_per_seg(ctx, c->n_seg, c->max_count_hint, 256), c->n_seg);
   k_gray_from_pts<<<grid, 256, 0, ctx->stream>>>(c->pts, c->count, c->gray, c->stride);
   LAUNCH_CHECK(ctx);
+  c->gray_valid = true;
   return RSPCL_OK;
 }
 
@@ -582,11 +593,7 @@ extern "C" int rspcl_crop35(rspcl_ctx* ctx, const rspcl_cloud* in, rspcl_cloud* 
   out->width = ow;
   out->height = oh;
   out->max_count_hint = ow * oh;
-  if (out->gray) {  // stale plane from a previous use of this handle
-    dim3 g2(blocks_per_seg(ctx, out->n_seg, ow * oh, 256), out->n_seg);
-    k_gray_from_pts<<<g2, 256, 0, ctx->stream>>>(out->pts, out->count, out->gray, out->stride);
-    LAUNCH_CHECK(ctx);
-  }
+  invalidate_gray(out);  // rebuilt lazily by the next edge extraction
   return RSPCL_OK;
 }
 

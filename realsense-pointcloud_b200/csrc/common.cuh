@@ -9,6 +9,8 @@
 #include <map>
 #include "../../include/rspcl.h"
 
+#define RSPCL_AUX_STREAMS 7
+
 struct rspcl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -27,6 +29,11 @@ struct rspcl_ctx {
   size_t z_cap = 0, z_used = 0;
   struct ZPending { void* dst; const void* src; size_t n; void* owned; };  // owned: pinned bounce buffer to free
   std::vector<ZPending> z_pending;
+  // forked streams for launches that run side by side (persistent ICP: one launch per cluster size)
+  cudaStream_t aux[RSPCL_AUX_STREAMS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[RSPCL_AUX_STREAMS] = {};
+  bool persist_ready = false;
+  double cluster_weight[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};  // SMs a cluster of c CTAs occupies (occupancy query)
   // point-sharded mode (comm.cu)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
@@ -76,6 +83,7 @@ struct rspcl_cloud {
   float4* pts = nullptr;   // [n_seg * stride] {x,y,z,rgba bits}
   int* count = nullptr;    // [n_seg] device-resident point counts
   uint8_t* gray = nullptr; // organized clouds: (r+g+b)/3 plane written by the upload kernel, [n_seg * stride]
+  bool gray_valid = false; // false: pts were rewritten since the plane was computed (ensure_gray rebuilds it lazily)
   int n_seg = 0;
   int stride = 0;
   int width = 0, height = 0;  // organized when height > 0
@@ -125,20 +133,68 @@ cudaError_t small_h2d(rspcl_ctx* ctx, void* d_dst, const void* h_src, size_t byt
 cudaError_t small_d2h(rspcl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);  // valid after ctx_sync()
 cudaError_t ctx_sync(rspcl_ctx* ctx);
 int comm_allreduce_f64(rspcl_ctx* ctx, double* buf, size_t n);
-// ICP nearest-neighbour cache handed from one align to the next align of the same pairs (icp.cu; owned by the caller)
-struct IcpCarry {
-  float4* work = nullptr;          // final working cloud of the previous align (.w = cached slot + 1 << 16 | index)
-  float* lb = nullptr;             // certified bounds at those positions
-  unsigned short* tslot = nullptr; // original target index behind every cached slot
-  const float4* tgt_pts = nullptr; // the target the cache refers to
-  double max_corr_dist = 0;
-  int S = 0, wstride = 0;
-  bool valid = false;
+// Options of the device-level ICP align (icp.cu)
+struct IcpAlignOpts {
+  int* d_corr_out = nullptr;                 // device correspondence dump [iteration][pair][stride] (match index or -1)
+  int corr_iters = 0;                        // iterations to dump (1 = PCL-style first correspondences)
+  rspcl_icp_result* h_results2 = nullptr;    // run a SECOND align from identity on the first one's output (icp:108-111)
+  const int* h_src_counts = nullptr;         // host copy of the source counts if the caller has one (saves a read-back)
+  const unsigned char* h_skip = nullptr;     // pairs to leave alone (finished elsewhere)
+  bool no_persist = false;                   // go straight to the global-memory path
 };
-void icp_carry_free(rspcl_ctx* ctx, IcpCarry* c);
+
+// Every stream-ordered scratch buffer of one call, released on EVERY exit path (error returns included).  A call that
+// returns an error without having reached its ctx_sync() may leave read-backs pending whose destinations are about to
+// go out of scope: unless ok() was called, the destructor drains the stream and drops them.
+struct Scratch {
+  rspcl_ctx* ctx;
+  std::vector<void*> ptrs;
+  bool fine = false;
+  explicit Scratch(rspcl_ctx* c) : ctx(c) {}
+  template <typename T>
+  cudaError_t alloc(T** p, size_t n) {
+    const cudaError_t e = scratch_alloc(ctx, p, n);
+    if (e == cudaSuccess) ptrs.push_back((void*)*p);
+    return e;
+  }
+  void ok() { fine = true; }
+  ~Scratch() {
+    if (!fine) {
+      cudaStreamSynchronize(ctx->stream);
+      for (auto& q : ctx->z_pending)
+        if (q.owned) cudaFreeHost(q.owned);
+      ctx->z_pending.clear();
+      ctx->z_used = 0;
+      cudaGetLastError();
+    }
+    for (void* q : ptrs) cudaFreeAsync(q, ctx->stream);
+  }
+};
+
+// scratch cloud batch (stream-ordered allocation)
+struct TmpCloud {
+  rspcl_cloud c;
+  rspcl_ctx* ctx;
+  explicit TmpCloud(rspcl_ctx* x) : ctx(x) {}
+  int init(int n_seg, int stride) {
+    c.n_seg = n_seg;
+    c.stride = stride;
+    c.max_count_hint = stride;
+    if (scratch_alloc(ctx, &c.pts, (size_t)n_seg * (stride ? stride : 1)) != cudaSuccess) return RSPCL_ERR_CUDA;
+    if (scratch_alloc(ctx, &c.count, (size_t)n_seg) != cudaSuccess) return RSPCL_ERR_CUDA;
+    return RSPCL_OK;
+  }
+  ~TmpCloud() {
+    scratch_free(ctx, c.pts);
+    scratch_free(ctx, c.count);
+    if (c.gray) cudaFree(c.gray);
+  }
+};
 int blocks_per_seg(const rspcl_ctx* ctx, int n_seg, int max_count, int threads);
 int transform_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float* d_T, int broadcast, rspcl_cloud* out);
 int ensure_gray(rspcl_ctx* ctx, rspcl_cloud* c);
+// an operation rewrote the colours of c->pts: the cached gray plane (if any) is stale
+static inline void invalidate_gray(rspcl_cloud* c) { c->gray_valid = false; }
 
 // ---- exclusive scan of int32 on the context stream (scan.cu) ----
 int rspcl_exclusive_scan_i32(rspcl_ctx* ctx, const int* in, int* out, long long n, int* total_out /* device, may be null */);

@@ -326,18 +326,18 @@ __device__ bool polar_rotation_fast(const double* A, double* R) {
   return false;
 }
 
-// pcl::umeyama(src, dst, with_scaling=false) from raw fp64 moments: S = {n, sum s, sum t, sum s_r t_c}
-__device__ void umeyama_from_moments(const double* S, float* T) {
-  const double n = S[0], inv_n = rcp_fast(n);
-  const double ms[3] = {S[1] * inv_n, S[2] * inv_n, S[3] * inv_n};
-  const double mt[3] = {S[4] * inv_n, S[5] * inv_n, S[6] * inv_n};
-  double sigma[9];  // sigma(r,c) = mean((t_r - mt_r)(s_c - ms_c))
+// Cold path of the rotation solve (scaled Newton in fp64, else Jacobi SVD with Umeyama's reflection fix), out of line and
+// with its operands passed BY VALUE: the hot path of the caller keeps sigma / R in registers and its instruction stream
+// short (one thread runs it once per ICP iteration; what it costs is instruction fetch and dependent latency).
+struct Mat3d {
+  double m[9];
+};
+__device__ __noinline__ Mat3d umeyama_rotation_slow(const Mat3d sg) {
+  Mat3d out;
+  double sigma[9], R[9];
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) sigma[r * 3 + c] = S[7 + c * 3 + r] * inv_n - mt[r] * ms[c];
-  double R[9];
-  if (!polar_rotation_fast(sigma, R) && !polar_rotation(sigma, R)) {
+  for (int i = 0; i < 9; ++i) sigma[i] = sg.m[i];
+  if (!polar_rotation(sigma, R)) {
     double U[9], sv[3], V[9];
     svd3(sigma, U, sv, V);
     const double d = det3(U) * det3(V);
@@ -352,6 +352,30 @@ __device__ void umeyama_from_moments(const double* S, float* T) {
         R[r * 3 + c] = acc;
       }
   }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out.m[i] = R[i];
+  return out;
+}
+
+// pcl::umeyama(src, dst, with_scaling=false) from raw fp64 moments: S = {n, sum s, sum t, sum s_r t_c}
+__device__ void umeyama_from_moments(const double* S, float* T) {
+  const double n = S[0], inv_n = rcp_fast(n);
+  const double ms[3] = {S[1] * inv_n, S[2] * inv_n, S[3] * inv_n};
+  const double mt[3] = {S[4] * inv_n, S[5] * inv_n, S[6] * inv_n};
+  double sigma[9];  // sigma(r,c) = mean((t_r - mt_r)(s_c - ms_c))
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sigma[r * 3 + c] = S[7 + c * 3 + r] * inv_n - mt[r] * ms[c];
+  double R[9];
+  if (!polar_rotation_fast(sigma, R)) {
+    Mat3d in;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) in.m[i] = sigma[i];
+    const Mat3d out = umeyama_rotation_slow(in);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = out.m[i];
+  }
   mat4_identity(T);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -362,7 +386,7 @@ __device__ void umeyama_from_moments(const double* S, float* T) {
 }
 
 __global__ void k_icp_init(IcpState* __restrict__ st, const float* __restrict__ guess, const double* __restrict__ prev_mse,
-                           int n_seg) {
+                           const unsigned char* __restrict__ skip, int n_seg) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_seg) return;
   IcpState S;
@@ -381,7 +405,7 @@ __global__ void k_icp_init(IcpState* __restrict__ st, const float* __restrict__ 
   S.iterations = 0;
   S.state = RSPCL_CONV_NOT_CONVERGED;
   S.converged = 0;
-  S.done = 0;
+  S.done = (skip && skip[s]) ? 1 : 0;  // pairs some other path has already finished are left alone by every kernel
   S.n_corr = 0;
   S.pad[0] = S.pad[1] = 0;
   st[s] = S;
@@ -470,7 +494,7 @@ __global__ void __launch_bounds__(IT) k_icp_step(float4* __restrict__ work, cons
                                                  const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
                                                  const float4* __restrict__ tgt, const int* __restrict__ tcount,
                                                  int tstride, double* __restrict__ partials,
-                                                 int* __restrict__ first_corr) {
+                                                 int* __restrict__ corr_out, int corr_iters) {
   __shared__ float M[16];
   __shared__ double s_red[IT / 32][NRED];
   __shared__ float4 tile[BRUTE ? IT : 1];
@@ -480,7 +504,9 @@ __global__ void __launch_bounds__(IT) k_icp_step(float4* __restrict__ work, cons
   const int apply = st[seg].apply_inc;
   if (threadIdx.x < 16) M[threadIdx.x] = st[seg].inc_T[threadIdx.x];
   __syncthreads();
-  const bool want_corr = first_corr != nullptr && st[seg].iterations == 0;
+  // correspondence dump [iteration][pair][stride] (match index or -1); corr_iters = 1: PCL-style first correspondences
+  const bool want_corr = corr_out != nullptr && st[seg].iterations < corr_iters;
+  int* first_corr = want_corr ? corr_out + (size_t)st[seg].iterations * gridDim.y * stride : nullptr;
   double acc[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
@@ -646,31 +672,6 @@ __global__ void k_pack_i32(const int* __restrict__ v, const int* __restrict__ co
 
 #include "icp_persist.cuh"
 
-// Working cloud of an align that continues a previous align of the same pairs (coarse -> fine, same source points moved
-// by the coarse result, same target): the new positions with the previous cache word (.w = slot + 1 << 16 | index) and
-// the previous bound lowered by the distance between the two positions of the point.
-__global__ void k_copy_work_carry(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
-                                  const float4* __restrict__ prev_work, const float* __restrict__ prev_lb,
-                                  float4* __restrict__ work, float* __restrict__ lb, int stride_work) {
-  const int seg = blockIdx.y;
-  const int n = count[seg];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float4 p = src[(size_t)seg * stride_src + i];
-    const float4 q = prev_work[(size_t)seg * stride_work + i];
-    float b = 0.f;
-    unsigned w = (unsigned)i;
-    if (finite3(p.x, p.y, p.z) && finite3(q.x, q.y, q.z)) {
-      b = prev_lb[(size_t)seg * stride_work + i] -
-          __fmaf_rn(sqrt_approx(dist2_l2simple(p.x, p.y, p.z, q.x, q.y, q.z)), 1.00001f, 1e-9f);
-      w = __float_as_uint(q.w);
-    }
-    p.w = __uint_as_float(w);
-    work[(size_t)seg * stride_work + i] = p;
-    lb[(size_t)seg * stride_work + i] = b;
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------
 // Certified-cache correspondence passes for clouds that do not fit the shared-memory kernel (global-memory grid).
 // Per source point: ci = position of its cached match inside g.sorted (-1: none), lb = lower bound of the true distance
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(IT) k_icp_stream(float4* __restrict__ work, co
                                                    const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
                                                    float* __restrict__ lb, int* __restrict__ ci,
                                                    int* __restrict__ wl, int* __restrict__ wlcount,
-                                                   double* __restrict__ partials, int* __restrict__ first_corr) {
+                                                   double* __restrict__ partials, int* __restrict__ corr_out, int corr_iters) {
   __shared__ float M[16];
   __shared__ double s_red[IT / 32][NRED];
   __shared__ int s_wcnt[2][IT / 32];
@@ -758,7 +759,8 @@ __global__ void __launch_bounds__(IT) k_icp_stream(float4* __restrict__ work, co
   const int apply = st[seg].apply_inc;
   if (threadIdx.x < 16) M[threadIdx.x] = st[seg].inc_T[threadIdx.x];
   __syncthreads();
-  const bool want_corr = first_corr != nullptr && st[seg].iterations == 0;
+  const bool want_corr = corr_out != nullptr && st[seg].iterations < corr_iters;
+  int* first_corr = want_corr ? corr_out + (size_t)st[seg].iterations * gridDim.y * stride : nullptr;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double acc[NRED];
 #pragma unroll
@@ -891,12 +893,13 @@ __global__ void __launch_bounds__(IT) k_icp_rescan(float4* __restrict__ work, co
                                                    const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
                                                    float* __restrict__ lb, int* __restrict__ ci,
                                                    const int* __restrict__ wl, const int* __restrict__ wloff,
-                                                   double* __restrict__ partials, int* __restrict__ first_corr) {
+                                                   double* __restrict__ partials, int* __restrict__ corr_out, int corr_iters) {
   __shared__ double s_red[IT / 32][NRED];
   const int seg = blockIdx.y;
   if (st[seg].done) return;
   const int n = count[seg];
-  const bool want_corr = first_corr != nullptr && st[seg].iterations == 0;
+  const bool want_corr = corr_out != nullptr && st[seg].iterations < corr_iters;
+  int* first_corr = want_corr ? corr_out + (size_t)st[seg].iterations * gridDim.y * stride : nullptr;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nblk = (int)gridDim.x;
   const int chunk = (((n + nblk - 1) / nblk + IT - 1) / IT) * IT;
@@ -940,6 +943,11 @@ __global__ void __launch_bounds__(IT) k_icp_rescan(float4* __restrict__ work, co
   }
 }
 
+
+// ---- launch plumbing of the persistent kernel
+typedef void (*PersistFn)(const PersistArgs, const IcpDevParams);
+PersistFn persist_fn(bool dbg) { return dbg ? k_icp_persist<true> : k_icp_persist<false>; }
+
 }  // namespace
 
 extern "C" void rspcl_icp_reference_params(rspcl_icp_params* p) {
@@ -951,27 +959,76 @@ extern "C" void rspcl_icp_reference_params(rspcl_icp_params* p) {
   p->mse_threshold_absolute = 1e-12;
 }
 
-// Device-level align used by rspcl_icp_align and the pairwise pipeline.  d_guess: n_seg x 16 floats on the device or
-// null.  h_results: host array (prev_mse read as input).  Synchronises before returning.
 int radix_sort_pairs(rspcl_ctx* ctx, unsigned long long* keys, int* vals, unsigned long long* tmp_keys, int* tmp_vals,
                      long long n);
 
-void icp_carry_free(rspcl_ctx* ctx, IcpCarry* c) {
-  scratch_free(ctx, c->work);
-  scratch_free(ctx, c->lb);
-  scratch_free(ctx, c->tslot);
-  *c = IcpCarry();
+// Per-pair cluster sizes for one batch (1..P_CLMAX CTAs per pair): the smallest cost bound L such that every pair can be
+// given enough CTAs to stay below it and the whole batch still fits one wave, i.e. the launch time (set by the pair with
+// the most expensive slice) is minimised and the chip is filled; left-over CTAs go to the most expensive slices.  The
+// cost of a slice is its length, doubled when it exceeds the P_CHUNK points a CTA keeps in registers (a streamed slice
+// re-reads and re-writes its points every iteration).  64 pairs of 4.5 - 12 k points on 148 SMs end up with 2, 3 or 4
+// CTAs each, every slice register-resident.
+static void plan_clusters(const std::vector<int>& cnt, double sm_count, const double* weight /* [P_CLMAX + 1]: SMs a cluster of c CTAs takes */,
+                          std::vector<int>* cl) {
+  const int S = (int)cnt.size();
+  cl->assign(S, 1);
+  if (S > (int)sm_count) return;  // several waves anyway: one CTA per pair
+  auto cost = [](int n, int c) {
+    const int len = (n + c - 1) / c;
+    return len > P_CHUNK ? 2 * len : len;
+  };
+  auto need = [&](int L, std::vector<int>* out) {
+    double tot = 0;
+    for (int s = 0; s < S; ++s) {
+      int c = 1;
+      while (c < P_CLMAX && cost(cnt[s], c) > L) ++c;
+      if (out) (*out)[s] = c;
+      tot += weight[c];
+    }
+    return tot;
+  };
+  int lo = P_THREADS, hi = 1;  // a slice below one point per thread gains nothing
+  for (int v : cnt) hi = 2 * v > hi ? 2 * v : hi;
+  if (hi < lo) hi = lo;
+  if (need(lo, nullptr) > sm_count) {
+    while (lo < hi) {  // smallest L with need(L) <= sm_count
+      const int mid = (lo + hi) / 2;
+      if (need(mid, nullptr) <= sm_count) hi = mid; else lo = mid + 1;
+    }
+  }
+  double used = need(lo, cl);
+  while (used < sm_count) {  // hand the remaining CTAs to the most expensive slices
+    int best = -1, bc = 0;
+    for (int s = 0; s < S; ++s) {
+      const int c = (*cl)[s];
+      if (c >= P_CLMAX || cnt[s] / (c + 1) < P_THREADS || used - weight[c] + weight[c + 1] > sm_count) continue;
+      const int v = cost(cnt[s], c);
+      if (v > bc) {
+        bc = v;
+        best = s;
+      }
+    }
+    if (best < 0) break;
+    used += weight[(*cl)[best] + 1] - weight[(*cl)[best]];
+    (*cl)[best] += 1;
+  }
 }
 
+// Device-level align used by rspcl_icp_align and the pairwise pipeline.  d_guess: n_seg x 16 floats on the device or
+// null.  h_results: host array (prev_mse read as input).  With o.h_results2 the call runs TWO aligns per pair: the second
+// from identity on the first one's output (the reference's coarse + fine ICP, icp:95 + icp:111), fused into one launch of
+// the persistent kernel when the pair fits it.  Synchronises before returning.
 int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
-                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, int* d_first_corr,
-                     IcpCarry* carry_out, const IcpCarry* carry_in) {
+                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, const IcpAlignOpts& o) {
   const int S = src->n_seg;
   const int shared_target = (tgt->n_seg == 1 && S > 1) ? 1 : 0;
   if (!shared_target && tgt->n_seg != S) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "icp_align: src has %d segments, tgt %d", S, tgt->n_seg);
   if (aligned && (aligned->n_seg != S || aligned->stride < src->max_count_hint))
     RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "icp_align: aligned output too small");
   if (prm->max_iterations < 1) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "icp_align: max_iterations < 1");
+  const bool two_stage = o.h_results2 != nullptr;
+  int* d_first_corr = o.d_corr_out;
+  const int corr_iters = o.d_corr_out ? (o.corr_iters > 0 ? o.corr_iters : 1) : 0;
 
   IcpDevParams dp;
   dp.max_iterations = prm->max_iterations;
@@ -987,38 +1044,50 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   dp.search_r = brute ? 0.f : (float)(prm->max_corr_dist * 1.01);
 
   const int wstride = src->stride ? src->stride : 1;
+  Scratch scr(ctx);  // every stream-ordered scratch buffer of this call: released on every exit path
   float4* work = nullptr;
-  IcpState* st = nullptr;
+  IcpState *st = nullptr, *st2 = nullptr;
   double *partials = nullptr, *d_prev = nullptr;
   int *n_active = nullptr, *d_range = nullptr;
   float* d_T = nullptr;
+  unsigned char* d_skip = nullptr;
   const int nblk = blocks_per_seg(ctx, S, src->max_count_hint, IT);
-  CU(ctx, scratch_alloc(ctx, &work, (size_t)S * wstride));
-  CU(ctx, scratch_alloc(ctx, &st, (size_t)S));
+  CU(ctx, scr.alloc(&work, (size_t)S * wstride));
+  CU(ctx, scr.alloc(&st, (size_t)S));
+  if (two_stage) CU(ctx, scr.alloc(&st2, (size_t)S));
   // global-memory path: certified-cache passes (k_icp_stream + k_icp_rescan) unless RSPCL_ICP_CACHE=0
   const char* cache_env = getenv("RSPCL_ICP_CACHE");
   const bool use_cache = !brute && !(cache_env && cache_env[0] == '0');
   const int nblk_total = use_cache ? 2 * nblk : nblk;
   float* g_lb = nullptr;
   int *g_ci = nullptr, *g_wl = nullptr, *g_wlcount = nullptr, *g_wloff = nullptr;
-  CU(ctx, scratch_alloc(ctx, &partials, (size_t)S * nblk_total * NRED));
-  CU(ctx, scratch_alloc(ctx, &d_prev, (size_t)S));
-  CU(ctx, scratch_alloc(ctx, &n_active, 1));
-  CU(ctx, scratch_alloc(ctx, &d_range, 1));
-  CU(ctx, scratch_alloc(ctx, &d_T, (size_t)S * 16));
+  CU(ctx, scr.alloc(&partials, (size_t)S * nblk_total * NRED));
+  CU(ctx, scr.alloc(&d_prev, (size_t)S));
+  CU(ctx, scr.alloc(&n_active, 1));
+  CU(ctx, scr.alloc(&d_range, 1));
+  CU(ctx, scr.alloc(&d_T, (size_t)S * 16));
   std::vector<double> prev(S);
+  int n_todo = S;
   for (int s = 0; s < S; ++s) prev[s] = h_results[s].prev_mse;
+  if (o.h_skip) {
+    CU(ctx, scr.alloc(&d_skip, (size_t)((S + 3) & ~3)));
+    std::vector<unsigned char> sk((size_t)((S + 3) & ~3), 0);
+    for (int s = 0; s < S; ++s) {
+      sk[s] = o.h_skip[s] ? 1 : 0;
+      n_todo -= sk[s];
+    }
+    CU(ctx, small_h2d(ctx, d_skip, sk.data(), sk.size()));
+  }
   CU(ctx, small_h2d(ctx, d_prev, prev.data(), S * sizeof(double)));
-  CU(ctx, small_h2d(ctx, n_active, &S, sizeof(int)));
+  CU(ctx, small_h2d(ctx, n_active, &n_todo, sizeof(int)));
   CU(ctx, cudaMemsetAsync(d_range, 0, sizeof(int), ctx->stream));
-  k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, S);
+  k_icp_init<<<div_up(S, 128), 128, 0, ctx->stream>>>(st, d_guess, d_prev, d_skip, S);
   LAUNCH_CHECK(ctx);
   dim3 gcopy(blocks_per_seg(ctx, S, src->max_count_hint, 256), S);
-  // Working cloud = source in SPATIAL order (radix sort by cell key), original index kept in .w: neighbouring lanes
-  // then probe neighbouring cells (coalesced / cached probes, far less divergence).  Sums are order-independent up to
-  // fp64 rounding; first_corr and the aligned output are written in original order.
-  // (The persistent kernel keeps its target in shared memory and, with the certified cache, scans only a few points per
-  // iteration, so it takes the source in its original order and skips the sort: ~1.2 ms per 64-pair step.)
+  // Working cloud of the GLOBAL-MEMORY path = source in SPATIAL order (radix sort by cell key), original index kept in
+  // .w: neighbouring lanes then probe neighbouring cells (coalesced / cached probes, far less divergence).  Sums are
+  // order-independent up to fp64 rounding; correspondences and the aligned output are written in original order.
+  // (The persistent kernel reads the source itself, unsorted, straight into registers.)
   const float sort_inv_cs = brute ? 10.0f : 1.0f / (float)(prm->max_corr_dist * 4.1);
   int* perm = nullptr;
   const int pstride = src->max_count_hint > 0 ? src->max_count_hint : 1;
@@ -1026,10 +1095,10 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     const long long N = (long long)S * pstride;
     unsigned long long *keys = nullptr, *tkeys = nullptr;
     int* tvals = nullptr;
-    CU(ctx, scratch_alloc(ctx, &keys, (size_t)N));
-    CU(ctx, scratch_alloc(ctx, &tkeys, (size_t)N));
-    CU(ctx, scratch_alloc(ctx, &perm, (size_t)N));
-    CU(ctx, scratch_alloc(ctx, &tvals, (size_t)N));
+    CU(ctx, scr.alloc(&keys, (size_t)N));
+    CU(ctx, scr.alloc(&tkeys, (size_t)N));
+    CU(ctx, scr.alloc(&perm, (size_t)N));
+    CU(ctx, scr.alloc(&tvals, (size_t)N));
     dim3 gk(blocks_per_seg(ctx, S, pstride, 256), S);
     k_source_keys<<<gk, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, pstride, sort_inv_cs, keys, perm);
     LAUNCH_CHECK(ctx);
@@ -1037,9 +1106,6 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     if (rcs) return rcs;
     k_copy_work_perm<<<gk, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, perm, pstride, work, wstride);
     LAUNCH_CHECK(ctx);
-    scratch_free(ctx, keys);
-    scratch_free(ctx, tkeys);
-    scratch_free(ctx, tvals);
     return RSPCL_OK;
   };
   const bool sharded = ctx->sharded_call && ctx->nccl_comm && ctx->nranks > 1;
@@ -1047,172 +1113,219 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   {
     const char* env = getenv("RSPCL_ICP_PERSIST");
     // (a target above the shared-memory capacity only sends ITS pair to the global-memory path, see below)
-    want_persist = !(env && env[0] == '0') && !sharded && !brute && src->max_count_hint > 0 && src->max_count_hint < 65536 &&
-                   (S > 1 || tgt->max_count_hint <= P_NTMAX);
+    want_persist = !(env && env[0] == '0') && !o.no_persist && !sharded && !brute && src->max_count_hint > 0 &&
+                   src->max_count_hint < 65536 && (S > 1 || tgt->max_count_hint <= P_NTMAX);
   }
+
+  // ---- persistent shared-memory path: one cluster per pair, all iterations (of both aligns) in one launch (icp_persist.cuh)
+  std::vector<unsigned char> finished(S, 0);  // pairs the persistent kernel has completed (all stages)
+  std::vector<IcpState> hst(S), hst2(two_stage ? S : 0);
+  int active_init = n_todo;  // pairs the global-memory path still has to run
+  double* totals = nullptr;
+  if (sharded) CU(ctx, scr.alloc(&totals, (size_t)S * NRED));
   if (want_persist) {
-    k_copy_work<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, work, wstride);
-    LAUNCH_CHECK(ctx);
-  } else {
+    if (!ctx->persist_ready) {
+      for (int d = 0; d < 2; ++d)
+        CU(ctx, cudaFuncSetAttribute(persist_fn(d != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
+      for (int a = 0; a < RSPCL_AUX_STREAMS; ++a) {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming));
+      }
+      CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      for (int c = 1; c <= P_CLMAX; ++c) {  // SMs a cluster of c CTAs effectively occupies = SMs / co-resident clusters
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3((unsigned)(c * ctx->sm_count));
+        q.blockDim = dim3(P_THREADS);
+        q.dynamicSmemBytes = sizeof(PersistSmem);
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = (unsigned)c;
+        qa[0].val.clusterDim.y = qa[0].val.clusterDim.z = 1;
+        q.attrs = qa;
+        q.numAttrs = 1;
+        int n_act = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_act, persist_fn(false), &q) != cudaSuccess || n_act <= 0) {
+          cudaGetLastError();
+          n_act = ctx->sm_count / c;
+        }
+        ctx->cluster_weight[c] = (double)ctx->sm_count / n_act;
+        if (ctx->cluster_weight[c] < c) ctx->cluster_weight[c] = c;
+      }
+      ctx->cluster_weight[0] = 0;
+      if (getenv("RSPCL_PERSIST_DBG"))
+        fprintf(stderr, "persist: SMs per cluster of 1..8 CTAs: %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f\n", ctx->cluster_weight[1], ctx->cluster_weight[2],
+                ctx->cluster_weight[3], ctx->cluster_weight[4], ctx->cluster_weight[5], ctx->cluster_weight[6], ctx->cluster_weight[7], ctx->cluster_weight[8]);
+      ctx->persist_ready = true;
+    }
+    int* d_status = nullptr;
+    CU(ctx, scr.alloc(&d_status, (size_t)S));
+    CU(ctx, cudaMemsetAsync(d_status, 0, (size_t)S * sizeof(int), ctx->stream));
+    std::vector<int> hcnt(S);
+    if (o.h_src_counts) {
+      for (int s = 0; s < S; ++s) hcnt[s] = o.h_src_counts[s];
+    } else {
+      CU(ctx, small_d2h(ctx, hcnt.data(), src->count, (size_t)S * sizeof(int)));
+      CU(ctx, ctx_sync(ctx));
+    }
+    // pairs in decreasing size (longest-processing-time-first), cluster size per pair, one launch per cluster size
+    std::vector<int> cl;
+    // SMs one wave may use: clusters of 3 or more do not tile every GPC, and a mix of sizes is placed greedily, so the
+    // planner charges every cluster size what the occupancy query says it takes and keeps two SMs in reserve (measured:
+    // a batch planned for all 148 SMs left a few clusters waiting for a second wave, +20 % launch time)
+    double budget = ctx->sm_count - 2;
+    if (const char* e = getenv("RSPCL_PERSIST_BUDGET")) budget = atof(e) > 0 ? atof(e) : budget;  // tuning knob
+    plan_clusters(hcnt, budget, ctx->cluster_weight, &cl);
+    std::vector<int> order;
+    int goff[P_CLMAX + 1], max_cl = 1;  // group gi holds the pairs with clusters of P_CLMAX - gi CTAs (largest first)
+    for (int gi = 0; gi < P_CLMAX; ++gi) {
+      goff[gi] = (int)order.size();
+      std::vector<int> grp;
+      for (int s = 0; s < S; ++s)
+        if (cl[s] == P_CLMAX - gi && !(o.h_skip && o.h_skip[s])) grp.push_back(s);
+      std::stable_sort(grp.begin(), grp.end(), [&](int a, int b) { return hcnt[a] > hcnt[b]; });
+      order.insert(order.end(), grp.begin(), grp.end());
+      if (!grp.empty() && P_CLMAX - gi > max_cl) max_cl = P_CLMAX - gi;
+    }
+    goff[P_CLMAX] = (int)order.size();
+    int* d_order = nullptr;
+    unsigned short* d_tidx = nullptr;  // original index of every cell-sorted target point (tie-breaks, correspondences)
+    float* d_lb = nullptr;             // streamed slices only: certified bounds between iterations
+    CU(ctx, scr.alloc(&d_tidx, (size_t)S * max_cl * P_NTMAX));  // one replica per CTA of a cluster
+    CU(ctx, scr.alloc(&d_lb, (size_t)S * wstride));
+    CU(ctx, scr.alloc(&d_order, order.size()));
+    if (!order.empty()) CU(ctx, small_h2d(ctx, d_order, order.data(), order.size() * sizeof(int)));
+    const bool want_dbg = getenv("RSPCL_PERSIST_DBG") != nullptr;
+    long long* d_dbg = nullptr;  // RSPCL_PERSIST_DBG=1: per-CTA phase cycle counters, printed to stderr
+    long long* d_dbg_iter = nullptr;
+    if (want_dbg) {
+      CU(ctx, scr.alloc(&d_dbg, (size_t)S * max_cl * 8));
+      CU(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)S * max_cl * 8 * sizeof(long long), ctx->stream));
+      CU(ctx, scr.alloc(&d_dbg_iter, (size_t)3 * 256));
+      CU(ctx, cudaMemsetAsync(d_dbg_iter, 0, (size_t)3 * 256 * sizeof(long long), ctx->stream));
+    }
+    PersistArgs pa;
+    pa.src = src->pts;
+    pa.count = src->count;
+    pa.sstride = src->stride;
+    pa.work = work;
+    pa.lb = d_lb;
+    pa.wstride = wstride;
+    pa.st1 = st;
+    pa.st2 = st2;
+    pa.n_stages = two_stage ? 2 : 1;
+    pa.tgt = tgt->pts;
+    pa.tcount = tgt->count;
+    pa.tstride = tgt->stride;
+    pa.shared_target = shared_target;
+    pa.inv_cs = 1.0f / (float)(prm->max_corr_dist * 4.1);
+    pa.corr_out = d_first_corr;
+    pa.corr_iters = corr_iters;
+    pa.n_pairs_total = S;
+    pa.status = d_status;
+    pa.order = d_order;
+    pa.tidx = d_tidx;
+    pa.tidx_rep = max_cl;
+    pa.dbg = d_dbg;
+    pa.dbg_iter = d_dbg_iter;
+    {
+      ProfScope prof(ctx, "k_icp_persist", 0.0);
+      // one launch per cluster size; the launches of a batch run side by side (largest clusters first: they are the
+      // hardest to place) on the context stream and forked streams
+      int n_groups = 0;
+      for (int gi = 0; gi < P_CLMAX; ++gi) n_groups += goff[gi + 1] > goff[gi] ? 1 : 0;
+      if (n_groups > 1) CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+      int used = 0;
+      for (int gi = 0; gi < P_CLMAX; ++gi) {
+        const int ng = goff[gi + 1] - goff[gi];
+        if (ng <= 0) continue;
+        const int gcl_i = P_CLMAX - gi;
+        cudaStream_t strm = used == 0 ? ctx->stream : ctx->aux[used - 1];
+        if (used > 0) CU(ctx, cudaStreamWaitEvent(strm, ctx->ev_fork, 0));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(gcl_i * ng));
+        cfg.blockDim = dim3(P_THREADS);
+        cfg.dynamicSmemBytes = sizeof(PersistSmem);
+        cfg.stream = strm;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)gcl_i;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        PersistArgs pg = pa;
+        pg.order = d_order + goff[gi];
+        CU(ctx, cudaLaunchKernelEx(&cfg, persist_fn(want_dbg), pg, dp));
+        LAUNCH_CHECK(ctx);
+        if (used > 0) {
+          CU(ctx, cudaEventRecord(ctx->ev_join[used - 1], strm));
+          CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[used - 1], 0));
+        }
+        ++used;
+      }
+      prof.end();
+      std::vector<int> hs(S);
+      CU(ctx, small_d2h(ctx, hs.data(), d_status, (size_t)S * sizeof(int)));
+      CU(ctx, small_d2h(ctx, hst.data(), st, (size_t)S * sizeof(IcpState)));
+      if (two_stage) CU(ctx, small_d2h(ctx, hst2.data(), st2, (size_t)S * sizeof(IcpState)));
+      CU(ctx, ctx_sync(ctx));
+      if (want_dbg) {
+        std::vector<long long> hd((size_t)S * max_cl * 8);
+        CU(ctx, cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<long long> hi3((size_t)3 * 256);
+        CU(ctx, cudaMemcpyAsync(hi3.data(), d_dbg_iter, hi3.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "persist dbg: per-iteration trace of the first CTA(s) [iteration: re-queried points, phase-B kcycles, iteration kcycles]\n");
+        for (int it = 0; it < 256 && hi3[3 * it + 2]; ++it)
+          fprintf(stderr, "  it %3d: %6lld %7.1f %7.1f\n", it, hi3[3 * it], hi3[3 * it + 1] / 1e3, hi3[3 * it + 2] / 1e3);
+        fprintf(stderr, "persist dbg: S=%d  [pair cl crank ns rescans iters | phaseA scan phaseB reduce+exchange solve head | total] kcycles\n", S);
+        for (int s = 0; s < S; ++s)
+          for (int c = 0; c < cl[s]; ++c) {
+            const long long* D = &hd[((size_t)s * max_cl + c) * 8];
+            fprintf(stderr, "  %3d %d %d %6d %6lld %3d | %7.1f %7.1f %7.1f %7.1f %7.1f %7.1f | %8.1f\n", s, cl[s], c, hcnt[s], D[6],
+                    hst[s].iterations + (two_stage ? hst2[s].iterations : 0), D[0] / 1e3, D[1] / 1e3, D[2] / 1e3, D[3] / 1e3,
+                    D[4] / 1e3, D[5] / 1e3, D[7] / 1e3);
+          }
+      }
+      int n_failed = 0;
+      double units = 0;
+      for (int s = 0; s < S; ++s) {
+        if (o.h_skip && o.h_skip[s]) continue;
+        if (hs[s]) {
+          ++n_failed;
+        } else {
+          finished[s] = 1;
+          units += (double)hcnt[s] * ((hst[s].iterations > 0 ? hst[s].iterations : 1) + (two_stage ? (hst2[s].iterations > 0 ? hst2[s].iterations : 1) : 0));
+        }
+      }
+      prof.set_units(units);
+      // Targets that did not fit the shared-memory grid (too many points / occupied cells) left the kernel before touching
+      // their state, so they are still freshly initialised; the finished pairs carry done = 1 and are skipped by every
+      // kernel of the global-memory path, which now runs for the remaining ones only.
+      active_init = n_failed;
+      if (n_failed) CU(ctx, small_h2d(ctx, n_active, &active_init, sizeof(int)));
+    }
+  }
+  const bool persist_done = want_persist && active_init == 0;
+  if (!persist_done) {
     const int rcs = build_sorted_work();
     if (rcs) return rcs;
   }
 
-  // ---- persistent shared-memory path: one cluster per pair, all iterations in one launch (icp_persist.cuh)
-  bool persist_done = false;
-  int active_init = S;  // pairs the global-memory path still has to run
-  double* totals = nullptr;
-  if (sharded) CU(ctx, scratch_alloc(ctx, &totals, (size_t)S * NRED));
-  {
-    if (want_persist) {
-      int* d_status = nullptr;
-      CU(ctx, scratch_alloc(ctx, &d_status, (size_t)S));
-      CU(ctx, cudaMemsetAsync(d_status, 0, (size_t)S * sizeof(int), ctx->stream));
-      // pairs in decreasing size (longest-processing-time-first) and a cluster size from a small cost model:
-      // t(CL) ~ 0.7 * 4/CL + 0.3 per pair (point loop scales with 1/CL, solve + barriers do not), slots = SMs / CL
-      std::vector<int> hcnt(S), order(S);
-      CU(ctx, small_d2h(ctx, hcnt.data(), src->count, (size_t)S * sizeof(int)));
-      CU(ctx, ctx_sync(ctx));
-      for (int s = 0; s < S; ++s) order[s] = s;
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hcnt[a] > hcnt[b]; });
-      int cl = 1;
-      {
-        double best = 1e30;
-        const int cands[3] = {4, 2, 1};
-        for (int c : cands) {
-          const double slots = (double)(ctx->sm_count / c) * (c == 4 ? 0.9 : 1.0);  // clusters of 4 do not tile every GPC
-          const double waves = (double)S / slots;
-          const double est = (0.7 * 4.0 / c + 0.3) * (waves > 1.0 ? waves : 1.0);
-          if (est < best) {
-            best = est;
-            cl = c;
-          }
-        }
-      }
-      int* d_order = nullptr;
-      unsigned short* d_tidx = nullptr;  // original index of every cell-sorted target point (tie-breaks, first_corr)
-      CU(ctx, scratch_alloc(ctx, &d_tidx, (size_t)S * 4 * P_NTMAX));  // one replica per CTA of a cluster (<= 4)
-      float* d_lb = nullptr;  // per-point certified lower bound of the distance to every non-cached target point
-      CU(ctx, scratch_alloc(ctx, &d_lb, (size_t)S * wstride));
-      // continue the cache of a previous align of the same pairs against the same target (coarse -> fine)?
-      const bool use_carry = carry_in && carry_in->valid && carry_in->S == S && carry_in->wstride == wstride &&
-                             carry_in->tgt_pts == tgt->pts && carry_in->max_corr_dist == prm->max_corr_dist && !d_first_corr;
-      unsigned short* d_ct = nullptr;  // target point behind every cached slot, for the next align (carry_out)
-      if (carry_out) CU(ctx, scratch_alloc(ctx, &d_ct, (size_t)S * wstride));
-      if (use_carry) {
-        k_copy_work_carry<<<gcopy, 256, 0, ctx->stream>>>(src->pts, src->count, src->stride, carry_in->work, carry_in->lb,
-                                                          work, d_lb, wstride);
-        LAUNCH_CHECK(ctx);
-      } else {
-        CU(ctx, cudaMemsetAsync(d_lb, 0, (size_t)S * wstride * sizeof(float), ctx->stream));
-      }
-      const unsigned short* d_ci = use_carry ? carry_in->tslot : nullptr;
-      CU(ctx, scratch_alloc(ctx, &d_order, (size_t)S));
-      CU(ctx, small_h2d(ctx, d_order, order.data(), (size_t)S * sizeof(int)));
-      const float inv_cs_p = 1.0f / (float)(prm->max_corr_dist * 4.1);
-      long long* d_dbg = nullptr;  // RSPCL_PERSIST_DBG=1: per-CTA phase cycle counters, printed to stderr
-      const bool want_dbg = getenv("RSPCL_PERSIST_DBG") != nullptr;
-      if (want_dbg) {
-        CU(ctx, scratch_alloc(ctx, &d_dbg, (size_t)S * 4 * 8));
-        CU(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)S * 4 * 8 * sizeof(long long), ctx->stream));
-      }
-      // (per device and cheap: set on every call rather than caching a per-process flag)
-      CU(ctx, cudaFuncSetAttribute(k_icp_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
-      CU(ctx, cudaFuncSetAttribute(k_icp_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
-      CU(ctx, cudaFuncSetAttribute(k_icp_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(cl * S));
-      cfg.blockDim = dim3(P_THREADS);
-      cfg.dynamicSmemBytes = sizeof(PersistSmem);
-      cfg.stream = ctx->stream;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = (unsigned)cl;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      const int* cnt_p = src->count;
-      const float4* tp = tgt->pts;
-      const int* tc = tgt->count;
-      int tstride_p = tgt->stride, ws = wstride, sh = shared_target;
-      ProfScope prof(ctx, "k_icp_persist", 0.0);
-      cudaError_t le;
-      if (cl == 4)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<4>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_ci, d_ct, d_dbg);
-      else if (cl == 2)
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<2>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_ci, d_ct, d_dbg);
-      else
-        le = cudaLaunchKernelEx(&cfg, k_icp_persist<1>, work, cnt_p, ws, st, tp, tc, tstride_p, sh, dp, inv_cs_p, d_first_corr, d_status, (const int*)d_order, d_lb, d_tidx, d_ci, d_ct, d_dbg);
-      CU(ctx, le);
-      LAUNCH_CHECK(ctx);
-      prof.end();
-      std::vector<int> hs(S);
-      std::vector<IcpState> hst0(S);
-      std::vector<int> hc(S);
-      CU(ctx, small_d2h(ctx, hs.data(), d_status, (size_t)S * sizeof(int)));
-      CU(ctx, small_d2h(ctx, hst0.data(), st, (size_t)S * sizeof(IcpState)));
-      CU(ctx, small_d2h(ctx, hc.data(), src->count, (size_t)S * sizeof(int)));
-      CU(ctx, ctx_sync(ctx));
-      if (want_dbg) {
-        std::vector<long long> hd((size_t)S * cl * 8);
-        CU(ctx, cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "persist dbg: S=%d cl=%d  [pair crank ns rescans iters | phaseA waitA phaseB reduce+exchange solve head | total] kcycles\n", S, cl);
-        for (int s = 0; s < S; ++s)
-          for (int c = 0; c < cl; ++c) {
-            const long long* D = &hd[((size_t)s * cl + c) * 8];
-            fprintf(stderr, "  %3d %d %6d %6lld %3d | %7.1f %7.1f %7.1f %7.1f %7.1f %7.1f | %8.1f\n", s, c, hc[s], D[6], hst0[s].iterations, D[0] / 1e3,
-                    D[1] / 1e3, D[2] / 1e3, D[3] / 1e3, D[4] / 1e3, D[5] / 1e3, D[7] / 1e3);
-          }
-        scratch_free(ctx, d_dbg);
-      }
-      scratch_free(ctx, d_status);
-      scratch_free(ctx, d_order);
-      scratch_free(ctx, d_tidx);
-      int n_failed = 0;
-      for (int s = 0; s < S; ++s) n_failed += hs[s] ? 1 : 0;
-      if (carry_out && n_failed == 0) {  // hand the working cloud, the bounds and the slot -> target map to the caller
-        carry_out->work = work;
-        carry_out->lb = d_lb;
-        carry_out->tslot = d_ct;
-        carry_out->S = S;
-        carry_out->wstride = wstride;
-        carry_out->tgt_pts = tgt->pts;
-        carry_out->max_corr_dist = prm->max_corr_dist;
-        carry_out->valid = true;
-        work = nullptr;
-      } else {
-        scratch_free(ctx, d_lb);
-        scratch_free(ctx, d_ct);
-      }
-      n_failed = 0;
-      double units = 0;
-      for (int s = 0; s < S; ++s) {
-        if (hs[s]) ++n_failed;
-        else units += (double)hc[s] * (hst0[s].iterations > 0 ? hst0[s].iterations : 1);
-      }
-      prof.set_units(units);
-      if (n_failed == 0) {
-        persist_done = true;
-      } else {
-        // Some targets did not fit the shared-memory grid (too many points / occupied cells).  Those pairs left the kernel
-        // before touching their state, so they are still freshly initialised; the finished pairs carry done = 1 and are
-        // skipped by every kernel of the global-memory path, which now runs for the remaining ones only.
-        active_init = n_failed;
-        CU(ctx, small_h2d(ctx, n_active, &active_init, sizeof(int)));
-        const int rcs = build_sorted_work();
-        if (rcs) return rcs;
-      }
-    }
-  }
-
   DevGrid g;
   g.shared_target = shared_target;
+  struct GridGuard {
+    rspcl_ctx* c;
+    DevGrid* g;
+    bool on = false;
+    ~GridGuard() { if (on) grid_free(c, g); }
+  } gguard{ctx, &g};
   if (!brute && !persist_done) {
     ProfScope prof(ctx, "grid_build", (double)S * tgt->max_count_hint);
     int rc = grid_build(ctx, tgt, cs, &g, d_range);
     if (rc) return rc;
+    gguard.on = true;
   }
 
   // iteration loop: launches are enqueued in growing chunks; the host only looks at the active-pair counter
@@ -1221,11 +1334,11 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   int done_iters = 0, chunk = 1, active = persist_done ? 0 : active_init;
   if (use_cache && !persist_done) {
     const size_t np = (size_t)S * wstride;
-    CU(ctx, scratch_alloc(ctx, &g_lb, np));
-    CU(ctx, scratch_alloc(ctx, &g_ci, np));
-    CU(ctx, scratch_alloc(ctx, &g_wl, np));
-    CU(ctx, scratch_alloc(ctx, &g_wlcount, (size_t)S * nblk));
-    CU(ctx, scratch_alloc(ctx, &g_wloff, (size_t)S * (nblk + 1)));
+    CU(ctx, scr.alloc(&g_lb, np));
+    CU(ctx, scr.alloc(&g_ci, np));
+    CU(ctx, scr.alloc(&g_wl, np));
+    CU(ctx, scr.alloc(&g_wlcount, (size_t)S * nblk));
+    CU(ctx, scr.alloc(&g_wloff, (size_t)S * (nblk + 1)));
     CU(ctx, cudaMemsetAsync(g_lb, 0, np * sizeof(float), ctx->stream));
     CU(ctx, cudaMemsetAsync(g_ci, 0xFF, np * sizeof(int), ctx->stream));
   }
@@ -1243,10 +1356,10 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         ProfScope prof(ctx, "k_icp_step", prof_units);
         if (brute)
           k_icp_step<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count,
-                                                         tgt->stride, partials, d_first_corr);
+                                                         tgt->stride, partials, d_first_corr, corr_iters);
         else if (!use_cache)
           k_icp_step<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, tgt->pts, tgt->count,
-                                                          tgt->stride, partials, d_first_corr);
+                                                          tgt->stride, partials, d_first_corr, corr_iters);
         LAUNCH_CHECK(ctx);
       }
       if (use_cache) {
@@ -1254,22 +1367,22 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
           ProfScope prof(ctx, "k_icp_stream", prof_units);
           if (done_iters == 0 && k == 0)
             k_icp_stream<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wlcount,
-                                                              partials, d_first_corr);
+                                                              partials, d_first_corr, corr_iters);
           else
             k_icp_stream<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wlcount,
-                                                               partials, d_first_corr);
+                                                               partials, d_first_corr, corr_iters);
           LAUNCH_CHECK(ctx);
         }
         ProfScope prof(ctx, "k_icp_rescan", prof_units);
         k_wl_offsets<<<S, 1024, 0, ctx->stream>>>(g_wlcount, nblk, st, g_wloff);
         LAUNCH_CHECK(ctx);
         k_icp_rescan<<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wloff,
-                                                    partials, d_first_corr);
+                                                    partials, d_first_corr, corr_iters);
         LAUNCH_CHECK(ctx);
       }
       ProfScope prof2(ctx, "k_icp_solve", (double)S);
       if (sharded) {
-        // partial sums of this rank's shard -> NCCL all-reduce over NVLink -> identical solve on every rank
+        // partial sums of this rank's shard -> all-reduce over NVLink -> identical solve on every rank
         k_icp_sum_partials<<<S, 32, 0, ctx->stream>>>(partials, nblk_total, st, totals);
         LAUNCH_CHECK(ctx);
         int rcc = comm_allreduce_f64(ctx, totals, (size_t)S * NRED);
@@ -1295,43 +1408,58 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     }
   }
   // results + aligned output (Registration::align: output = final applied to the original source)
-  std::vector<IcpState> hst(S);
   int range = 0;
-  CU(ctx, small_d2h(ctx, hst.data(), st, S * sizeof(IcpState)));
+  if (!persist_done) CU(ctx, small_d2h(ctx, hst.data(), st, S * sizeof(IcpState)));
   CU(ctx, small_d2h(ctx, &range, d_range, sizeof(int)));
   int rc = RSPCL_OK;
-  if (aligned) {
+  // pairs of a two-stage call that the persistent kernel could not take: their first align has just run on the
+  // global-memory path; the second one follows below as a separate align on the first one's output
+  bool need_stage2 = false;
+  if (two_stage)
+    for (int s = 0; s < S; ++s) need_stage2 = need_stage2 || (!finished[s] && !(o.h_skip && o.h_skip[s]));
+  TmpCloud mid(ctx);
+  if (aligned || need_stage2) {
     k_gather_final<<<div_up(S * 16, 256), 256, 0, ctx->stream>>>(st, d_T, S);
     LAUNCH_CHECK(ctx);
-    rc = transform_device(ctx, src, d_T, 0, aligned);
+    if (aligned) rc = transform_device(ctx, src, d_T, 0, aligned);
+    if (!rc && need_stage2) {
+      rc = mid.init(S, wstride);
+      if (!rc) rc = transform_device(ctx, src, d_T, 0, &mid.c);
+    }
   }
   CU(ctx, ctx_sync(ctx));
-  for (int s = 0; s < S; ++s) {
-    memcpy(h_results[s].T, hst[s].final_T, sizeof(float) * 16);
-    h_results[s].converged = hst[s].converged;
-    h_results[s].state = hst[s].state;
-    h_results[s].iterations = hst[s].iterations;
-    h_results[s].n_corr = hst[s].n_corr;
-    h_results[s].mse = hst[s].mse;
-    h_results[s].prev_mse = hst[s].prev_mse;
-  }
-  if (!brute && !persist_done) grid_free(ctx, &g);
-  scratch_free(ctx, work);
-  scratch_free(ctx, st);
-  scratch_free(ctx, partials);
-  scratch_free(ctx, d_prev);
-  scratch_free(ctx, n_active);
-  scratch_free(ctx, d_range);
-  scratch_free(ctx, d_T);
-  scratch_free(ctx, totals);
-  scratch_free(ctx, perm);
-  scratch_free(ctx, g_lb);
-  scratch_free(ctx, g_ci);
-  scratch_free(ctx, g_wl);
-  scratch_free(ctx, g_wlcount);
-  scratch_free(ctx, g_wloff);
   if (rc) return rc;
   if (range) RSPCL_FAIL(ctx, RSPCL_ERR_RANGE, "icp_align: target coordinates exceed the grid key range (+-32767 cells of %g m)", cs);
+  auto put = [](rspcl_icp_result& r, const IcpState& h) {
+    memcpy(r.T, h.final_T, sizeof(float) * 16);
+    r.converged = h.converged;
+    r.state = h.state;
+    r.iterations = h.iterations;
+    r.n_corr = h.n_corr;
+    r.mse = h.mse;
+    r.prev_mse = h.prev_mse;
+  };
+  for (int s = 0; s < S; ++s) {
+    if (o.h_skip && o.h_skip[s]) continue;
+    put(h_results[s], hst[s]);
+    if (two_stage && finished[s]) put(o.h_results2[s], hst2[s]);
+  }
+  if (need_stage2) {
+    std::vector<rspcl_icp_result> r2(S);
+    std::vector<unsigned char> skip2(S);
+    for (int s = 0; s < S; ++s) {
+      r2[s] = o.h_results2[s];  // prev_mse input
+      skip2[s] = (finished[s] || (o.h_skip && o.h_skip[s])) ? 1 : 0;
+    }
+    IcpAlignOpts o2;
+    o2.h_skip = skip2.data();
+    o2.no_persist = true;  // these pairs did not fit the shared-memory kernel
+    rc = icp_align_device(ctx, &mid.c, tgt, prm, nullptr, r2.data(), nullptr, o2);
+    if (rc) return rc;
+    for (int s = 0; s < S; ++s)
+      if (!skip2[s]) o.h_results2[s] = r2[s];
+  }
+  scr.ok();
   return RSPCL_OK;
 }
 
@@ -1346,10 +1474,13 @@ int refresh_count_hint(rspcl_ctx* ctx, const rspcl_cloud* c, std::vector<int>* c
   return RSPCL_OK;
 }
 
-extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
-                               const float* guess, rspcl_icp_result* results, rspcl_cloud* aligned, int32_t* first_corr) {
+// shared body of rspcl_icp_align / rspcl_icp_align_dump: host_corr receives n_dump iterations of correspondences, each
+// packed like a download of src
+static int icp_align_host(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
+                          const float* guess, rspcl_icp_result* results, rspcl_cloud* aligned, int n_dump, int32_t* host_corr) {
   if (!ctx || !src || !tgt || !prm || !results) return RSPCL_ERR_ARG;
   if (aligned == tgt) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "icp_align: aligned must not alias the target");
+  if (host_corr && n_dump < 1) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "icp_align: n_dump_iterations < 1");
   CU(ctx, cudaSetDevice(ctx->device));
   std::vector<int> scnt;
   int rc = refresh_count_hint(ctx, src, &scnt);
@@ -1357,15 +1488,25 @@ extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rsp
   rc = refresh_count_hint(ctx, tgt, nullptr);
   if (rc) return rc;
   const int S = src->n_seg;
+  const size_t wstride = src->stride ? src->stride : 1;
+  Scratch scr(ctx);
   float* d_guess = nullptr;
   int* d_fc = nullptr;
   if (guess) {
-    CU(ctx, scratch_alloc(ctx, &d_guess, (size_t)S * 16));
+    CU(ctx, scr.alloc(&d_guess, (size_t)S * 16));
     CU(ctx, small_h2d(ctx, d_guess, guess, (size_t)S * 16 * sizeof(float)));
   }
-  if (first_corr) CU(ctx, scratch_alloc(ctx, &d_fc, (size_t)S * (src->stride ? src->stride : 1)));
-  rc = icp_align_device(ctx, src, tgt, prm, d_guess, results, aligned, d_fc, nullptr, nullptr);
-  if (!rc && first_corr) {
+  if (host_corr) {
+    CU(ctx, scr.alloc(&d_fc, (size_t)n_dump * S * wstride));
+    // iterations that are never executed (early convergence) read as -1
+    CU(ctx, cudaMemsetAsync(d_fc, 0xFF, (size_t)n_dump * S * wstride * sizeof(int), ctx->stream));
+  }
+  IcpAlignOpts o;
+  o.d_corr_out = d_fc;
+  o.corr_iters = n_dump;
+  o.h_src_counts = scnt.data();
+  rc = icp_align_device(ctx, src, tgt, prm, d_guess, results, aligned, o);
+  if (!rc && host_corr) {
     std::vector<int> off(S);
     long long total = 0;
     for (int s = 0; s < S; ++s) {
@@ -1374,21 +1515,32 @@ extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rsp
     }
     if (total) {
       int *d_off = nullptr, *packed = nullptr;
-      CU(ctx, scratch_alloc(ctx, &d_off, (size_t)S));
-      CU(ctx, scratch_alloc(ctx, &packed, (size_t)total));
+      CU(ctx, scr.alloc(&d_off, (size_t)S));
+      CU(ctx, scr.alloc(&packed, (size_t)total * n_dump));
       CU(ctx, small_h2d(ctx, d_off, off.data(), S * sizeof(int)));
       dim3 grid(blocks_per_seg(ctx, S, src->max_count_hint, 256), S);
-      k_pack_i32<<<grid, 256, 0, ctx->stream>>>(d_fc, src->count, d_off, src->stride, packed);
-      LAUNCH_CHECK(ctx);
-      CU(ctx, small_d2h(ctx, first_corr, packed, (size_t)total * sizeof(int)));
+      for (int it = 0; it < n_dump; ++it) {
+        k_pack_i32<<<grid, 256, 0, ctx->stream>>>(d_fc + (size_t)it * S * wstride, src->count, d_off, src->stride,
+                                                  packed + (size_t)it * total);
+        LAUNCH_CHECK(ctx);
+      }
+      CU(ctx, small_d2h(ctx, host_corr, packed, (size_t)total * n_dump * sizeof(int)));
       CU(ctx, ctx_sync(ctx));
-      scratch_free(ctx, d_off);
-      scratch_free(ctx, packed);
     }
   }
-  scratch_free(ctx, d_guess);
-  scratch_free(ctx, d_fc);
+  if (!rc) scr.ok();
   return rc;
+}
+
+extern "C" int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
+                               const float* guess, rspcl_icp_result* results, rspcl_cloud* aligned, int32_t* first_corr) {
+  return icp_align_host(ctx, src, tgt, prm, guess, results, aligned, 1, first_corr);
+}
+
+extern "C" int rspcl_icp_align_dump(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
+                                    const float* guess, rspcl_icp_result* results, int n_dump_iterations, int32_t* host_corr) {
+  if (!host_corr) return RSPCL_ERR_ARG;
+  return icp_align_host(ctx, src, tgt, prm, guess, results, nullptr, n_dump_iterations, host_corr);
 }
 
 extern "C" int rspcl_icp_align_sharded(rspcl_ctx* ctx, const rspcl_cloud* src_shard, const rspcl_cloud* tgt,

@@ -11,8 +11,7 @@
 #include <float.h>
 
 int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
-                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, int* d_first_corr,
-                     IcpCarry* carry_out, const IcpCarry* carry_in);
+                     const float* d_guess, rspcl_icp_result* h_results, rspcl_cloud* aligned, const IcpAlignOpts& o);
 int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_ndt_params* prm,
                      const float* d_guess, rspcl_ndt_result* h_results, rspcl_cloud* aligned);
 int voxel_approx_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float leaf[3], rspcl_cloud* out);
@@ -61,24 +60,6 @@ __global__ void k_transform2_gather(const float4* __restrict__ frames, int w_h, 
   }
 }
 
-struct TmpCloud {
-  rspcl_cloud c;
-  rspcl_ctx* ctx;
-  explicit TmpCloud(rspcl_ctx* x) : ctx(x) {}
-  int init(int n_seg, int stride) {
-    c.n_seg = n_seg;
-    c.stride = stride;
-    c.max_count_hint = stride;
-    if (scratch_alloc(ctx, &c.pts, (size_t)n_seg * (stride ? stride : 1)) != cudaSuccess) return RSPCL_ERR_CUDA;
-    if (scratch_alloc(ctx, &c.count, (size_t)n_seg) != cudaSuccess) return RSPCL_ERR_CUDA;
-    return RSPCL_OK;
-  }
-  ~TmpCloud() {
-    scratch_free(ctx, c.pts);
-    scratch_free(ctx, c.count);
-  }
-};
-
 }  // namespace
 
 extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, const int32_t* src_idx, const int32_t* tgt_idx,
@@ -110,32 +91,36 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
   const int pstride = E.c.max_count_hint > 0 ? E.c.max_count_hint : 1;
 
   // 3. pair-major batches
+  Scratch scr(ctx);
   int *d_src = nullptr, *d_tgt = nullptr;
-  CU(ctx, scratch_alloc(ctx, &d_src, (size_t)n_pairs));
-  CU(ctx, scratch_alloc(ctx, &d_tgt, (size_t)n_pairs));
+  CU(ctx, scr.alloc(&d_src, (size_t)n_pairs));
+  CU(ctx, scr.alloc(&d_tgt, (size_t)n_pairs));
   CU(ctx, small_h2d(ctx, d_src, src_idx, n_pairs * sizeof(int)));
   CU(ctx, small_h2d(ctx, d_tgt, tgt_idx, n_pairs * sizeof(int)));
-  TmpCloud Sc(ctx), Tc(ctx), Ac(ctx);
-  if (Sc.init(n_pairs, pstride) || Tc.init(n_pairs, pstride) || Ac.init(n_pairs, pstride))
+  TmpCloud Sc(ctx), Tc(ctx);
+  if (Sc.init(n_pairs, pstride) || Tc.init(n_pairs, pstride))
     RSPCL_FAIL(ctx, RSPCL_ERR_CUDA, "register_pairs: scratch allocation failed");
   dim3 gg(blocks_per_seg(ctx, n_pairs, pstride, 256), n_pairs);
   k_gather_segments<<<gg, 256, 0, ctx->stream>>>(E.c.pts, E.c.count, E.c.stride, d_src, Sc.c.pts, Sc.c.count, pstride);
   LAUNCH_CHECK(ctx);
   k_gather_segments<<<gg, 256, 0, ctx->stream>>>(E.c.pts, E.c.count, E.c.stride, d_tgt, Tc.c.pts, Tc.c.count, pstride);
   LAUNCH_CHECK(ctx);
+  Sc.c.max_count_hint = Tc.c.max_count_hint = pstride;
+  std::vector<int> scnt(n_pairs);
+  for (int i = 0; i < n_pairs; ++i) scnt[i] = vcnt[src_idx[i]] < pstride ? vcnt[src_idx[i]] : pstride;
 
-  // 4. coarse stage
+  // 4. coarse stage + 5. fine ICP from identity on the coarse-aligned source
   float* d_guess = nullptr;
   if (guess) {
-    CU(ctx, scratch_alloc(ctx, &d_guess, (size_t)n_pairs * 16));
+    CU(ctx, scr.alloc(&d_guess, (size_t)n_pairs * 16));
     CU(ctx, small_h2d(ctx, d_guess, guess, (size_t)n_pairs * 16 * sizeof(float)));
   }
   std::vector<float> hT((size_t)n_pairs * 32);
   std::vector<rspcl_icp_result> fine(n_pairs);
-  // The fine align runs on the same pairs against the same targets, its source being the coarse source moved by the
-  // coarse result: it inherits the coarse align's certified nearest-neighbour cache instead of re-querying every point.
-  IcpCarry carry;
+  for (auto& r : fine) r.prev_mse = DBL_MAX;
   if (coarse_kind == RSPCL_COARSE_NDT) {
+    TmpCloud Ac(ctx);
+    if (Ac.init(n_pairs, pstride)) RSPCL_FAIL(ctx, RSPCL_ERR_CUDA, "register_pairs: scratch allocation failed");
     std::vector<rspcl_ndt_result> nr(n_pairs);
     rc = ndt_align_device(ctx, &Sc.c, &Tc.c, ndt, d_guess, nr.data(), &Ac.c);
     if (rc) return rc;
@@ -143,24 +128,26 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
       memcpy(results[i].T_coarse, nr[i].T, 64);
       results[i].coarse_iterations = nr[i].iterations;
     }
+    IcpAlignOpts o;
+    o.h_src_counts = scnt.data();
+    rc = icp_align_device(ctx, &Ac.c, &Tc.c, icp, nullptr, fine.data(), nullptr, o);
+    if (rc) return rc;
   } else {
+    // coarse and fine ICP of every pair in ONE launch of the persistent kernel: the fine align runs on the same pairs
+    // against the same targets, its source being the original source moved by the coarse result, so it keeps the
+    // target replica and the certified nearest-neighbour cache of the coarse align
     std::vector<rspcl_icp_result> cr(n_pairs);
     for (auto& r : cr) r.prev_mse = DBL_MAX;
-    rc = icp_align_device(ctx, &Sc.c, &Tc.c, icp, d_guess, cr.data(), &Ac.c, nullptr, &carry, nullptr);
-    if (rc) {
-      icp_carry_free(ctx, &carry);
-      return rc;
-    }
+    IcpAlignOpts o;
+    o.h_results2 = fine.data();
+    o.h_src_counts = scnt.data();
+    rc = icp_align_device(ctx, &Sc.c, &Tc.c, icp, d_guess, cr.data(), nullptr, o);
+    if (rc) return rc;
     for (int i = 0; i < n_pairs; ++i) {
       memcpy(results[i].T_coarse, cr[i].T, 64);
       results[i].coarse_iterations = cr[i].iterations;
     }
   }
-  // 5. fine ICP from identity on the coarse-aligned source
-  for (auto& r : fine) r.prev_mse = DBL_MAX;
-  rc = icp_align_device(ctx, &Ac.c, &Tc.c, icp, nullptr, fine.data(), nullptr, nullptr, nullptr, &carry);
-  icp_carry_free(ctx, &carry);
-  if (rc) return rc;
   std::vector<int> accept(n_pairs);
   for (int i = 0; i < n_pairs; ++i) {
     memcpy(results[i].T_fine, fine[i].T, 64);
@@ -174,12 +161,12 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
     memcpy(&hT[(size_t)i * 16], results[i].T_coarse, 64);
     memcpy(&hT[(size_t)(n_pairs + i) * 16], results[i].T_fine, 64);
   }
-  // 6. full-cloud transform of the accepted frames
+  // 6. full-cloud transform of the accepted frames (stream-ordered: the call returns without waiting for it)
   if (out_transformed) {
     float* d_T = nullptr;
     int* d_acc = nullptr;
-    CU(ctx, scratch_alloc(ctx, &d_T, (size_t)n_pairs * 32));
-    CU(ctx, scratch_alloc(ctx, &d_acc, (size_t)n_pairs));
+    CU(ctx, scr.alloc(&d_T, (size_t)n_pairs * 32));
+    CU(ctx, scr.alloc(&d_acc, (size_t)n_pairs));
     CU(ctx, small_h2d(ctx, d_T, hT.data(), hT.size() * sizeof(float)));
     CU(ctx, small_h2d(ctx, d_acc, accept.data(), n_pairs * sizeof(int)));
     dim3 gt(blocks_per_seg(ctx, n_pairs, npx, 256), n_pairs);
@@ -191,12 +178,8 @@ extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, c
     out_transformed->width = frames->width;
     out_transformed->height = frames->height;
     out_transformed->max_count_hint = npx;
-    CU(ctx, ctx_sync(ctx));  // hT / accept are host vectors about to go out of scope
-    scratch_free(ctx, d_T);
-    scratch_free(ctx, d_acc);
+    invalidate_gray(out_transformed);
   }
-  scratch_free(ctx, d_src);
-  scratch_free(ctx, d_tgt);
-  scratch_free(ctx, d_guess);
+  scr.ok();
   return RSPCL_OK;
 }

@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_PKG, "librspcl_b200.so")
+SO_PATH = os.environ.get("RSPCL_LIB") or os.path.join(_PKG, "librspcl_b200.so")  # RSPCL_LIB: A/B-test another build
 
 POINT = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])           # RSPCL_LAYOUT_PCD16
 PCL32 = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("w", "<f4"), ("rgba", "<u4"),
@@ -64,7 +64,7 @@ EXPORTS = [
     "rspcl_cloud_destroy", "rspcl_cloud_n_seg", "rspcl_cloud_stride", "rspcl_cloud_dims", "rspcl_cloud_upload",
     "rspcl_cloud_counts", "rspcl_cloud_download", "rspcl_crop35", "rspcl_edge_extract", "rspcl_voxel_approx",
     "rspcl_voxel_keys", "rspcl_transform", "rspcl_concat", "rspcl_cloud_copy_segment", "rspcl_icp_reference_params",
-    "rspcl_icp_align", "rspcl_fitness", "rspcl_nearest", "rspcl_ndt_reference_params", "rspcl_ndt_align",
+    "rspcl_icp_align", "rspcl_icp_align_dump", "rspcl_fitness", "rspcl_nearest", "rspcl_ndt_reference_params", "rspcl_ndt_align",
     "rspcl_ndt_voxels", "rspcl_ndt_derivatives", "rspcl_register_pairs", "rspcl_comm_unique_id", "rspcl_comm_init",
     "rspcl_comm_destroy", "rspcl_icp_align_sharded", "rspcl_ndt_align_sharded",
 ]
@@ -364,6 +364,22 @@ def icp_align(ctx, src, tgt, prm=None, guess=None, prev_mse=None, want_aligned=T
     out = [{"T": c_to_mat(r.T), "converged": bool(r.converged), "state": r.state, "iterations": r.iterations,
             "n_corr": r.n_corr, "mse": r.mse, "prev_mse": r.prev_mse} for r in res]
     return out, aligned, fc
+
+
+def icp_align_dump(ctx, src, tgt, prm=None, guess=None, n_iters=1):
+    """Per-iteration correspondences (match index or -1) of the first n_iters iterations: [n_iters, total points]."""
+    prm = prm or icp_params()
+    S = src.n_seg
+    res = (IcpResult * S)()
+    for s in range(S):
+        res[s].prev_mse = DBL_MAX
+    g = mats_to_c(guess, S) if guess is not None else None
+    total = max(int(src.counts().sum()), 1)
+    corr = np.zeros((n_iters, total), np.int32)
+    ctx.check(lib().rspcl_icp_align_dump(ctx.h, src.h, tgt.h, C.byref(prm), _p(g), res, int(n_iters), _p(corr)))
+    out = [{"T": c_to_mat(r.T), "converged": bool(r.converged), "state": r.state, "iterations": r.iterations,
+            "n_corr": r.n_corr, "mse": r.mse, "prev_mse": r.prev_mse} for r in res]
+    return out, corr
 
 
 def ndt_align(ctx, src, tgt, prm=None, guess=None, want_aligned=True):
