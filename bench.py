@@ -6,14 +6,21 @@ A step = one pass of the registration hot path over one synthetic sweep per GPU:
 settings: -30 deg initial guess, 50 forced coarse + 50 forced fine iterations, 1 cm approximate voxel filter,
 1 cm correspondence gate) including the full-cloud transformPointCloud of every source frame.
 
-  value  : device-resident throughput (frames already in HBM as device clouds), CUDA events on the library stream.
-  e2e    : the same step through the C ABI with HOST buffers: pinned pcl::PointXYZRGB (32 B/pt) frames uploaded and the
-           transformed full clouds downloaded inside the timed region.
+  value  : device-resident throughput (frames already in HBM as device clouds; the gray plane of the Canny input is
+           rebuilt inside every step), CUDA events on the library stream.
+  e2e    : the same step through the C ABI with HOST buffers inside the timed region: pinned frames uploaded, transformed
+           full clouds downloaded.  Headline leg = the 16-byte `.pcd` row layout (x y z rgb: what the reference's
+           --registration mode reads from and writes to disk, main.cpp:81,87, and what the CPU reference arm holds);
+           `e2e_pcl32` = the same with pcl::PointXYZRGB's 32-byte in-memory layout (12 of every 32 bytes are padding).
   roofline: the ICP correspondence+reduction kernel (k_icp_persist: all iterations of a batch of pairs in one launch;
            k_icp_stream on the global-memory path), algorithmic bytes = 32 B per source point per iteration,
            timed with CUDA events bracketing each launch in one extra, untimed-for-`value` step.
   ndt    : (rank 0, N=1) BASELINE configs[2] on the side: one 1280x720 pair, 0.05 m voxels -> ms per NDT iteration and per
            derivative evaluation (the metric also names "ms per ICP/NDT iteration").
+  configs0: (rank 0, N=1) BASELINE configs[0], the reference's literal `rs-pcl --registration` path: 3 frames, NDT coarse +
+           ICP fine with the reference's own epsilons, accumulating target (rspcl_register_sequence) next to the oracle.
+  point_sharded: BASELINE configs[4]: one 50 M-point pair, source sharded over the N ranks, 17 fp64 partial sums per
+           iteration all-reduced over NVLink; ms per iteration, roofline fraction, spread over ranks, difference to 1 GPU.
   cpu_baseline: the oracle (CPU port of the reference's PCL path) on a bounded sample of the same sweep, 1 thread.
   --impl reference: the oracle with all host threads (one pair per thread) -- the reference arm.
 
@@ -41,7 +48,7 @@ RADS = -0.523599  # icp_edge_based_registration.hpp:135
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=65, help="frames per GPU sweep (pairs = frames - 1); 65 = a 64-pair sweep (configs[3])")
@@ -51,6 +58,11 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=24, help="pairs in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ndt", action="store_true", help="skip the side measurement of configs[2] (NDT, 1280x720)")
+    ap.add_argument("--no-configs0", action="store_true", help="skip the literal rs-pcl --registration leg (configs[0])")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the point-sharded leg (configs[4])")
+    ap.add_argument("--sharded-points", type=int, default=50_000_000, help="points of the source AND of the target of the point-sharded leg")
+    ap.add_argument("--sharded-iters", type=int, default=30)
+    ap.add_argument("--sharded-gate", type=float, default=0.002)
     ap.add_argument("--e2e-contexts", type=int, default=4)
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--e2e-lock", default="nosync", choices=["sync", "nosync", "none"],
@@ -178,7 +190,7 @@ def run_reference(a, rank, world):
         return
     import gen_scene
     threads = host_threads()
-    n_pairs = max(8, min(2 * threads, 64))
+    n_pairs = a.frames - 1  # the GPU arm's pairs per step, whatever the host (same config on both arms)
     frames, _ = gen_scene.make_sweep(a.seed, min(n_pairs + 1, 17))
     # bounded sample: reuse the generated frames cyclically so generation stays short
     idx = [k % len(frames) for k in range(n_pairs + 1)]
@@ -190,7 +202,8 @@ def run_reference(a, rank, world):
         dt, _ = cpu_sweep_pairs(fr, n_pairs, a.iters, a.coarse, threads)
         total += dt
     val = a.steps * n_pairs / total
-    sample = "%d pairs/step x %d steps, %d threads (one pair per thread), oracle port of the PCL path" % (n_pairs, a.steps, threads)
+    sample = ("%d pairs/step x %d steps, %d threads (one pair per thread), oracle port of the PCL path; the sweep reuses %d "
+              "generated frames cyclically" % (n_pairs, a.steps, threads, len(frames)))
     print(json.dumps({
         "impl": "reference", "metric": "frame-pair registrations/sec @640x480", "value": val, "unit": "pairs/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
@@ -235,6 +248,265 @@ def bind_to_gpu_numa_node(torch, dev):
         return "no binding (%s)" % type(e).__name__
 
 
+# ---------------------------------------------------------------------------------------------- side legs
+def pcie_ceiling(torch, dist, world):
+    """What the box's host<->device path gives when every rank moves data at once: 256 MiB pinned buffers, H2D and D2H on
+    two streams at the same time, all ranks started together.  Returns (this rank's GB/s per direction, aggregate GB/s
+    per direction over the ranks) -- the denominator of the e2e figure, which is transfer-bound."""
+    n = 256 << 20
+    h_a = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_b = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_b = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+
+    both()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        both()
+        both()
+        torch.cuda.synchronize()
+        best = min(best, (time.perf_counter() - t0) / 2)
+    mine = n / 1e9 / best
+    agg = mine
+    if dist is not None:
+        t = torch.tensor([mine], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        agg = float(t.item())
+    return mine, agg
+
+
+def ndt_config2_leg(ctx, R, gen_scene, guess, hbm_peak):
+    """BASELINE configs[2]: edge-based NDT on one 1280x720 pair (921,600 points per frame), 0.05 m voxels."""
+    W2, H2 = 1280, 720
+    fr2, T2 = gen_scene.make_sweep(3, 2, W2, H2, noise_scale=0.2)
+    d2 = ctx.upload(list(fr2), W2, H2)
+    v2 = R.voxel_approx(ctx, R.edge_extract(ctx, d2)).download()
+    s2, t2 = ctx.upload([v2[1]]), ctx.upload([v2[0]])
+    p2 = R.ndt_params(resolution=0.05)
+    R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
+    ctx.profile_reset()
+    ctx.profile(True)
+    ctx.timer_start()
+    r2, _ = R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
+    ms2 = ctx.timer_stop()
+    ctx.profile(False)
+    ke, kc = ctx.profile_get("k_ndt_eval"), ctx.profile_get("k_ndt_control")
+    kp = ctx.profile_get("k_ndt_persist")
+    ang2, tr2 = pose_err(r2[0]["T"], gen_scene.pairwise_gt(T2, 1))
+    leg = {"workload": "configs[2]: edge-based NDT, one 1280x720 pair (921,600 points per frame), 0.05 m voxels, step 0.1, eps 0.01",
+           "edge_points_src_tgt": [int(len(v2[1])), int(len(v2[0]))], "iterations": r2[0]["iterations"],
+           "derivative_evals": r2[0]["n_derivative_evals"], "converged": bool(r2[0]["converged"]),
+           "ms_align": ms2, "ms_per_ndt_iteration": ms2 / max(r2[0]["iterations"], 1),
+           "err_vs_ground_truth_rad_m": [ang2, tr2]}
+    evals = max(r2[0]["n_derivative_evals"] + r2[0]["n_hessian_evals"], 1)
+    if kp["launches"]:
+        leg["ms_per_derivative_eval"] = kp["ms"] / evals
+        leg["kernel"] = "k_ndt_persist (all evaluations of the align in one launch)"
+        # units = (source point, neighbour voxel) pairs the evaluations touched, in gradient-evaluation equivalents
+        # (~135 fp64 operations per pair, ~456 when the Hessian is evaluated too: counted from ndt_point_eval in
+        # csrc/ndt.cu); bytes per pair: 16 B source point + 72 B voxel (mean + inverse covariance)
+        pairs = kp["units"]
+        flops = pairs * 135.0
+        fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12  # B200: 64 fp64 FMA / clk / SM
+        leg["roofline"] = {"bound": "fp64 (latency / launch-bound at ~6 k points: see note)", "point_voxel_pairs": pairs,
+                           "gflops": flops / (kp["ms"] / 1e3) / 1e9 if kp["ms"] > 0 else None,
+                           "frac_fp64": (flops / (kp["ms"] / 1e3) / 1e12) / fp64_peak if kp["ms"] > 0 else None,
+                           "fp64_peak_tflops_nominal": fp64_peak,
+                           "hbm_frac": (pairs * 88.0 / (kp["ms"] / 1e3) / 1e9) / hbm_peak if kp["ms"] > 0 else None,
+                           "note": "one 6 k-point pair occupies one cluster: the align is bound by the dependent chain of the "
+                                   "Newton / More-Thuente evaluations, not by the FP64 pipe or HBM; the pipe fraction is what a "
+                                   "batch of pairs multiplies"}
+    else:
+        leg["ms_per_derivative_eval"] = ke["ms"] / max(ke["launches"], 1)
+        leg["ms_per_control_step"] = kc["ms"] / max(kc["launches"], 1)
+    return leg
+
+
+def configs0_leg(ctx, R, gen_scene, a):
+    """BASELINE configs[0]: `rs-pcl --registration` on 3 synthetic 640x480 frames with the reference's literal settings --
+    NDT coarse (eps 0.01, step 0.1, 1 m voxels, <= 50 iterations) + ICP fine (eps 1 / 1000: one iteration), -30 deg per
+    frame, accumulating target -- through rspcl_register_sequence, next to the oracle's line-by-line scheme on one thread."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    fr3, T3 = gen_scene.make_sweep(1, 3)
+    n = len(fr3)
+    guesses = np.stack([np.eye(4)] * n)
+    acc = np.float32(0)
+    for k in range(1, n):
+        acc = np.float32(acc + np.float32(RADS))
+        guesses[k][:3, :3] = gen_scene.rot_y(float(acc))
+    h_in = ctx.pinned(n * NPX * 16)
+    h_in.view(R.POINT)[:] = np.concatenate(list(fr3))
+    h_out = ctx.pinned(n * NPX * 16)
+    cnt = np.full(n, NPX, np.int32)
+    d_fr = ctx.cloud(n, NPX)
+    d_out = ctx.cloud(1, n * NPX)
+    import ctypes as C
+    L = R.lib()
+    oc = np.zeros(1, np.int32)
+
+    def up():
+        d_fr.upload_raw(h_in.ctypes.data_as(C.c_void_p), cnt, W, H, R.LAYOUT_PCD16)
+
+    def run():
+        d_fr.invalidate_gray()
+        return R.register_sequence(ctx, d_fr, guesses, R.COARSE_NDT, out_global=d_out)[0]
+
+    def down():
+        ctx.check(L.rspcl_cloud_download(ctx.h, d_out.h, h_out.ctypes.data_as(C.c_void_p), R.LAYOUT_PCD16, C.c_longlong(n * NPX),
+                                         oc.ctypes.data_as(C.c_void_p)))
+
+    up()
+    res = run()
+    reps = 10
+    ctx.timer_start()
+    for _ in range(reps):
+        res = run()
+    ms_dev = ctx.timer_stop() / reps
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        up()
+        run()
+        down()
+    ms_e2e = 1e3 * (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    o = orc.scheme_edge(fr3.reshape(-1), W, H, "ndt")
+    cpu_s = time.perf_counter() - t0
+    errs_o, errs_gt = [], []
+    for k in range(1, n):
+        T = R.c_to_mat(res[k].T_fine).astype(np.float64) @ R.c_to_mat(res[k].T_coarse).astype(np.float64)
+        errs_o.append(pose_err(T, o["T"][k]))
+        errs_gt.append(pose_err(T, T3[k]))
+    return {"workload": "configs[0]: rs-pcl --registration, 3 frames 640x480, NDT coarse + ICP fine, reference-literal settings, "
+                        "-30 deg per frame, accumulating target (rspcl_register_sequence)",
+            "registrations": n - 1, "accepted": [int(r.converged) for r in res],
+            "ndt_iterations": [int(r.coarse_iterations) for r in res[1:]],
+            "gpu_ms_device_resident": ms_dev, "gpu_ms_e2e_host_pcd16": ms_e2e,
+            "pairs_per_s_device_resident": (n - 1) / (ms_dev / 1e3), "pairs_per_s_e2e": (n - 1) / (ms_e2e / 1e3),
+            "cpu_baseline": {"value": (n - 1) / cpu_s, "unit": "pairs/s", "cores": 1, "kind": "port",
+                             "sample": "the same 3 frames, oracle scheme (orc_scheme_edge), single thread, %.2f s" % cpu_s},
+            "speedup_e2e_vs_cpu_1_thread": cpu_s * 1e3 / ms_e2e,
+            "max_err_vs_oracle_rad_m_frame1": [float(errs_o[0][0]), float(errs_o[0][1])],
+            "max_err_vs_oracle_rad_m_later_frames": [float(max(e[0] for e in errs_o[1:])), float(max(e[1] for e in errs_o[1:]))],
+            "max_err_vs_ground_truth_rad_m": [float(max(e[0] for e in errs_gt)), float(max(e[1] for e in errs_gt))],
+            "note": "frames >= 2 of a chained NDT differ from the oracle's own chain at the method's accuracy (ulp-level chaos of "
+                    "the iteration count, tests/test_gpu_facade.py); every stage matches the oracle to 1e-4 on identical inputs"}
+
+
+def point_sharded_leg(ctx, R, gen_scene, torch, dist, rank, world, dev, a, hbm_peak):
+    """BASELINE configs[4]: one pair of --sharded-points points each (uniform samples of the room surface); the source is
+    split over the ranks, the target replicated; per iteration the 17 fp64 partial sums are all-reduced on the library
+    stream and every rank runs the identical solve.  Rank 0 then aligns the WHOLE source alone for the 1-vs-N check."""
+    P, iters = a.sharded_points, a.sharded_iters
+    if world > 1:
+        uid = torch.from_numpy(R.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        R.comm_init(ctx, world, rank, uid.cpu().numpy())
+    tgt = gen_scene.sample_room_surface(a.seed + 77, P)
+    Tm = np.eye(4)
+    Tm[:3, :3] = gen_scene.rot_axis([0.3, 1.0, 0.2], 0.0004)
+    Tm[:3, 3] = [0.0006, -0.0004, 0.0005]
+    Ti = np.linalg.inv(Tm)
+
+    def shard(r):  # source shard r: its own seeded sample, moved by the inverse of the transform the align must recover
+        lo, hi = r * P // world, (r + 1) * P // world
+        s0 = gen_scene.sample_room_surface(a.seed + 78 + r, hi - lo)
+        xyz = np.stack([s0["x"], s0["y"], s0["z"]], 1).astype(np.float64) @ Ti[:3, :3].T + Ti[:3, 3]
+        s0["x"], s0["y"], s0["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        return s0
+
+    d_tgt = ctx.upload([tgt])
+    d_src = ctx.upload([shard(rank)])
+    prm = R.icp_params(max_iterations=iters, max_corr_dist=a.sharded_gate, transformation_epsilon=-1.0,
+                       euclidean_fitness_epsilon=-1e300, mse_threshold_absolute=-1.0)
+    R.icp_align_sharded(ctx, d_src, d_tgt, prm)  # warm-up (pool growth, NCCL channels)
+    if dist is not None:
+        dist.barrier()
+    ctx.profile_reset()
+    ctx.profile(True)
+    ctx.timer_start()
+    res = R.icp_align_sharded(ctx, d_src, d_tgt, prm)[0][0]
+    ms = ctx.timer_stop()
+    ctx.profile(False)
+    ks, kr, ka = ctx.profile_get("k_icp_stream"), ctx.profile_get("k_icp_rescan"), ctx.profile_get("allreduce")
+    ksol = ctx.profile_get("k_icp_solve")
+    # the same align with the partial sums going through ncclAllReduce instead of the peer-memory exchange
+    nccl_cmp = None
+    if dist is not None:
+        os.environ["RSPCL_PEER_XCHG"] = "0"
+        R.icp_align_sharded(ctx, d_src, d_tgt, prm)
+        dist.barrier()
+        ctx.profile_reset()
+        ctx.profile(True)
+        ctx.timer_start()
+        res_n = R.icp_align_sharded(ctx, d_src, d_tgt, prm)[0][0]
+        ms_n = ctx.timer_stop()
+        ctx.profile(False)
+        ka_n, ksol_n = ctx.profile_get("allreduce"), ctx.profile_get("k_icp_solve")
+        del os.environ["RSPCL_PEER_XCHG"]
+        tn = torch.tensor([ms_n], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        nccl_cmp = {"ms_per_iteration": float(tn.item()) / max(res_n["iterations"], 1),
+                    "sum_allreduce_solve_us_per_iteration": 1e3 * ksol_n["ms"] / max(ksol_n["launches"], 1),
+                    "ncclAllReduce_us_per_iteration": 1e3 * ka_n["ms"] / max(ka_n["launches"], 1) if ka_n["launches"] else None,
+                    "same_transform_as_peer_path": bool(np.array_equal(res_n["T"], res["T"]))}
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    Tall = torch.from_numpy(res["T"].astype(np.float64)).cuda().reshape(1, 16)
+    spread = 0.0
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(Tall) for _ in range(world)]
+        dist.all_gather(gathered, Tall)
+        spread = max(float((g - Tall).abs().max()) for g in gathered)
+    out = None
+    if rank == 0:
+        ms_all = float(t.item())
+        # algorithmic bytes: 32 B per source point per iteration (SURVEY 8d), all ranks' points, against N x the HBM peak
+        ach = 32.0 * P * res["iterations"] / (ms_all / 1e3) / 1e9
+        ach_stream = 32.0 * ks["units"] / (ks["ms"] / 1e3) / 1e9 if ks["ms"] > 0 else None
+        out = {"workload": "configs[4]: point-sharded ICP, %d-point source sharded over %d GPU(s), %d-point target replicated, "
+                           "gate %.4f m, %d forced iterations" % (P, world, P, a.sharded_gate, iters),
+               "n_gpus": world, "iterations": int(res["iterations"]), "ms_total": ms_all,
+               "ms_per_iteration": ms_all / max(res["iterations"], 1),
+               "stream_kernel_ms_per_launch": ks["ms"] / max(ks["launches"], 1),
+               "rescan_ms_per_launch": kr["ms"] / max(kr["launches"], 1),
+               "exchange": ("one-shot peer-memory all-reduce over NVLink fused with the solve (k_icp_solve_peer)" if world > 1 and not ka["launches"]
+                            else ("ncclAllReduce" if world > 1 else "none (1 GPU)")),
+               "sum_exchange_solve_us_per_iteration": 1e3 * ksol["ms"] / max(ksol["launches"], 1),
+               "allreduce_bytes_per_iteration": 17 * 8,
+               "nccl_allreduce_variant": nccl_cmp,
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak * world, "unit": "GB/s", "frac": ach / (hbm_peak * world),
+                            "stream_kernel_frac_this_rank": (ach_stream / hbm_peak) if ach_stream else None,
+                            "note": "whole iteration (streaming pass + exact re-queries + solve + all-reduce), 32 algorithmic "
+                                    "bytes per source point, all ranks, against N x the measured HBM peak"},
+               "n_corr": int(res["n_corr"]), "max_T_spread_over_ranks": spread,
+               "max_abs_T_error_vs_ground_truth": float(np.abs(res["T"].astype(np.float64) - Tm).max())}
+        if world > 1:
+            c1 = R.Context(dev)
+            whole = np.concatenate([shard(r) for r in range(world)])
+            r1 = R.icp_align(c1, c1.upload([whole]), c1.upload([tgt]), prm, want_aligned=False)[0][0]
+            out["diff_vs_1gpu_max_abs_T"] = float(np.abs(r1["T"].astype(np.float64) - res["T"].astype(np.float64)).max())
+            out["n_corr_1gpu"] = int(r1["n_corr"])
+            c1.close()
+    if dist is not None:
+        dist.barrier()
+        R.comm_destroy(ctx)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     a = parse()
@@ -270,10 +542,14 @@ def main():
     src_idx = np.arange(1, F, dtype=np.int32)
     tgt_idx = np.arange(0, F - 1, dtype=np.int32)
 
-    # pinned host frames in pcl::PointXYZRGB layout (what the reference holds in memory) + pinned result buffer
-    h_in = ctx.pinned(F * NPX * 32)
-    h_in.view(R.PCL32)[:] = np.concatenate([R.to_pcl32(f) for f in frames])
-    h_out = ctx.pinned(n_pairs * NPX * 32)
+    # pinned host frames in both host layouts + pinned result buffers
+    LAY = {"pcd16": (R.LAYOUT_PCD16, R.POINT, 16), "pcl32": (R.LAYOUT_PCL32, R.PCL32, 32)}
+    h_in, h_out = {}, {}
+    for name, (_, dt, esz) in LAY.items():
+        h_in[name] = ctx.pinned(F * NPX * esz)
+        h_out[name] = ctx.pinned(n_pairs * NPX * esz)
+    h_in["pcd16"].view(R.POINT)[:] = np.concatenate(list(frames))
+    h_in["pcl32"].view(R.PCL32)[:] = np.concatenate([R.to_pcl32(f) for f in frames])
     counts = np.full(F, NPX, np.int32)
     d_frames = ctx.cloud(F, NPX)
     d_out = ctx.cloud(n_pairs, NPX)
@@ -282,13 +558,14 @@ def main():
     import ctypes as C
 
     def upload():
-        d_frames.upload_raw(h_in.ctypes.data_as(C.c_void_p), counts, W, H, R.LAYOUT_PCL32)
+        d_frames.upload_raw(h_in["pcd16"].ctypes.data_as(C.c_void_p), counts, W, H, R.LAYOUT_PCD16)
 
     def step():
+        d_frames.invalidate_gray()  # the (r+g+b)/3 plane of the Canny input is rebuilt inside the step
         return R.register_pairs(ctx, d_frames, src_idx, tgt_idx, coarse, icp=icp, ndt=ndt, guess=guess, out_transformed=d_out)
 
     def download():
-        ctx.check(L.rspcl_cloud_download(ctx.h, d_out.h, h_out.ctypes.data_as(C.c_void_p), R.LAYOUT_PCL32,
+        ctx.check(L.rspcl_cloud_download(ctx.h, d_out.h, h_out["pcd16"].ctypes.data_as(C.c_void_p), R.LAYOUT_PCD16,
                                          C.c_longlong(n_pairs * NPX), out_counts.ctypes.data_as(C.c_void_p)))
 
     def barrier():
@@ -338,6 +615,7 @@ def main():
     # several contexts (one stream + one host thread each), so chunk c+1's H2D, chunk c's kernels and chunk c-1's D2H
     # overlap (PCIe is full duplex).  Every frame still crosses PCIe (a chunk re-uploads its one boundary frame).
     from concurrent.futures import ThreadPoolExecutor
+    import contextlib
     n_ctx = a.e2e_contexts
     n_chunks = max(d for d in range(1, a.e2e_chunks + 1) if n_pairs % d == 0)  # equal chunks keep the batch shape fixed
     cp = n_pairs // n_chunks
@@ -346,68 +624,105 @@ def main():
     for w in range(n_ctx):
         cw = ctx if w == 0 else R.Context(dev)
         workers.append({"ctx": cw, "frames": cw.cloud(cp + 1, NPX), "out": cw.cloud(cp, NPX), "oc": np.zeros(cp, np.int32)})
-    in_rows = h_in.view(R.PCL32).reshape(F, NPX)
-    out_rows = h_out.view(R.PCL32).reshape(n_pairs, NPX)
     cnts = np.full(cp + 1, NPX, np.int32)
     si = np.arange(1, cp + 1, dtype=np.int32)
     ti = np.arange(0, cp, dtype=np.int32)
-
-    def run_chunks(w, steps, timed):
-        """Worker w streams its chunks for `steps` consecutive steps (no barrier between steps: the e2e timed region
-        is one continuous pipeline of steps x chunks, bracketed once on both sides)."""
-        W_ = workers[w]
-        cw = W_["ctx"]
-        if timed:
-            cw.timer_start()
-        for st_i in range(steps):
-            for ci in range(w, n_chunks, n_ctx):
-                lo, hi = chunks[ci]
-                # frames lo .. hi: pair i registers frame i+1 onto frame i
-                # one transfer per direction at a time: the contexts fall into a staggered pipeline (A computes while B
-                # uploads and C downloads) instead of moving in lockstep and sharing each PCIe direction
-                t0 = time.perf_counter()
-                with h2d_lock:
-                    t1 = time.perf_counter()
-                    W_["frames"].upload_raw(in_rows[lo:hi + 1].ctypes.data_as(C.c_void_p), cnts, W, H, R.LAYOUT_PCL32)
-                    if a.e2e_lock == "sync":
-                        cw.sync()
-                t2 = time.perf_counter()
-                R.register_pairs(cw, W_["frames"], si, ti, coarse, icp=icp, ndt=ndt, guess=guess, out_transformed=W_["out"])
-                t3 = time.perf_counter()
-                with d2h_lock:
-                    t4 = time.perf_counter()
-                    cw.check(L.rspcl_cloud_download(cw.h, W_["out"].h, out_rows[lo:hi].ctypes.data_as(C.c_void_p),
-                                                    R.LAYOUT_PCL32, C.c_longlong(cp * NPX), W_["oc"].ctypes.data_as(C.c_void_p)))
-                t5 = time.perf_counter()
-                if timed and a.e2e_trace:
-                    trace.append((w, st_i, ci, t0, t1, t2, t3, t4, t5))
-        if timed:
-            cw.timer_mark()
-
-    import contextlib
     h2d_lock, d2h_lock = (contextlib.nullcontext(), contextlib.nullcontext()) if a.e2e_lock == "none" else (threading.Lock(), threading.Lock())
-    trace = []
     pool = ThreadPoolExecutor(n_ctx)
-    list(pool.map(lambda w: run_chunks(w, max(1, a.warmup - 1), False), range(n_ctx)))
-    barrier()
-    list(pool.map(lambda w: run_chunks(w, a.steps, True), range(n_ctx)))
-    ms_e2e = max_over_ranks(R.timer_span([w["ctx"] for w in workers]))
-    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and e2e)
-    if a.e2e_trace and trace:
-        tz = min(t[3] for t in trace)
-        for t in sorted(trace, key=lambda t: t[3]):
-            sys.stderr.write("ctx %d step %d chunk %d: wait_h2d %.2f upload %.2f compute %.2f wait_d2h %.2f download %.2f  [start %.2f end %.2f ms]\n" % (
-                t[0], t[1], t[2], 1e3 * (t[4] - t[3]), 1e3 * (t[5] - t[4]), 1e3 * (t[6] - t[5]), 1e3 * (t[7] - t[6]),
-                1e3 * (t[8] - t[7]), 1e3 * (t[3] - tz), 1e3 * (t[8] - tz)))
-    barrier()
-    e2e = world * n_pairs * a.steps / (ms_e2e / 1e3)
+    trace = []
+
+    def e2e_leg(name, xyz_mode=None):
+        """One timed e2e region in host layout `name`; xyz_mode (pcl32 only): download x y z 1 only (0: 2-D DMA, 1: kernel
+        stores into the pinned buffer), the caller's buffer keeping its colours."""
+        lay, dt, esz = LAY[name]
+        in_rows = h_in[name].view(dt).reshape(F, NPX)
+        out_rows = h_out[name].view(dt).reshape(n_pairs, NPX)
+
+        def run_chunks(w, steps, timed):
+            W_ = workers[w]
+            cw = W_["ctx"]
+            if timed:
+                cw.timer_start()
+            for st_i in range(steps):
+                for ci in range(w, n_chunks, n_ctx):
+                    lo, hi = chunks[ci]
+                    # one transfer per direction at a time: the contexts fall into a staggered pipeline (A computes while B
+                    # uploads and C downloads) instead of moving in lockstep and sharing each PCIe direction
+                    t0 = time.perf_counter()
+                    with h2d_lock:
+                        t1 = time.perf_counter()
+                        W_["frames"].upload_raw(in_rows[lo:hi + 1].ctypes.data_as(C.c_void_p), cnts, W, H, lay)
+                        if a.e2e_lock == "sync":
+                            cw.sync()
+                    t2 = time.perf_counter()
+                    R.register_pairs(cw, W_["frames"], si, ti, coarse, icp=icp, ndt=ndt, guess=guess, out_transformed=W_["out"])
+                    t3 = time.perf_counter()
+                    with d2h_lock:
+                        t4 = time.perf_counter()
+                        if xyz_mode is None:
+                            cw.check(L.rspcl_cloud_download(cw.h, W_["out"].h, out_rows[lo:hi].ctypes.data_as(C.c_void_p), lay,
+                                                            C.c_longlong(cp * NPX), W_["oc"].ctypes.data_as(C.c_void_p)))
+                        else:
+                            cw.check(L.rspcl_cloud_download_xyz_pcl32(cw.h, W_["out"].h, out_rows[lo:hi].ctypes.data_as(C.c_void_p),
+                                                                      C.c_longlong(cp * NPX), int(xyz_mode)))
+                    t5 = time.perf_counter()
+                    if timed and a.e2e_trace:
+                        trace.append((name, w, st_i, ci, t0, t1, t2, t3, t4, t5))
+            if timed:
+                cw.timer_mark()
+
+        list(pool.map(lambda w: run_chunks(w, max(1, a.warmup - 1), False), range(n_ctx)))
+        barrier()
+        list(pool.map(lambda w: run_chunks(w, a.steps, True), range(n_ctx)))
+        ms_leg = max_over_ranks(R.timer_span([w["ctx"] for w in workers]))
+        barrier()
+        d2h = n_pairs * NPX * (esz if xyz_mode is None else 16) + n_pairs * 160
+        return {"value": world * n_pairs * a.steps / (ms_leg / 1e3), "unit": "pairs/s", "layout": name,
+                "h2d_bytes_per_step": (n_pairs + len(chunks)) * NPX * esz, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_leg / a.steps}, out_rows
+
+    e2e16, rows16 = e2e_leg("pcd16")
     # the pipelined path must reproduce the single-context result
-    chk = R.from_pcl32(out_rows[0])
+    chk = rows16[0].copy()
     download()
-    ref0 = R.from_pcl32(h_out.view(R.PCL32).reshape(n_pairs, NPX)[0])
-    # (bit equality is not guaranteed: the cluster size, hence the fp64 summation order, depends on the batch size)
+    ref0 = h_out["pcd16"].view(R.POINT).reshape(n_pairs, NPX)[0]
+    # (bit equality is not guaranteed: the cluster sizes, hence the fp64 summation order, depend on the batch size)
     dmax = max(float(np.abs(chk[a_] - ref0[a_]).max()) for a_ in "xyz")
     assert dmax < 1e-5 and np.array_equal(chk["rgba"], ref0["rgba"]), "pipelined e2e result differs from the single-context result"
+    e2e32, rows32 = e2e_leg("pcl32")
+    assert np.array_equal(rows32[0]["rgba"], ref0["rgba"]) and max(float(np.abs(rows32[0][a_] - ref0[a_]).max()) for a_ in "xyz") < 1e-5
+    # PCL32, x y z only: transformPointCloud changes 12 of the 32 bytes of a point; is a strided 16-of-32-byte read-back
+    # (2-D DMA copy or a kernel storing over PCIe) faster than moving all 32?  Measured on one chunk, the faster way is kept.
+    probe = None
+    if rank == 0 and world == 1:
+        cw, Wk = workers[0]["ctx"], workers[0]
+        Wk["frames"].upload_raw(h_in["pcl32"].view(R.PCL32).reshape(F, NPX)[0:cp + 1].ctypes.data_as(C.c_void_p), cnts, W, H, R.LAYOUT_PCL32)
+        R.register_pairs(cw, Wk["frames"], si, ti, coarse, icp=icp, ndt=ndt, guess=guess, out_transformed=Wk["out"])
+        cw.sync()
+        probe = {"points": cp * NPX}
+        dst = rows32[0:cp]
+        for label, fn in (("full_32B", lambda: cw.check(L.rspcl_cloud_download(cw.h, Wk["out"].h, dst.ctypes.data_as(C.c_void_p), R.LAYOUT_PCL32, C.c_longlong(cp * NPX), Wk["oc"].ctypes.data_as(C.c_void_p)))),
+                          ("xyz_2d_dma", lambda: cw.check(L.rspcl_cloud_download_xyz_pcl32(cw.h, Wk["out"].h, dst.ctypes.data_as(C.c_void_p), C.c_longlong(cp * NPX), 0))),
+                          ("xyz_kernel_store", lambda: cw.check(L.rspcl_cloud_download_xyz_pcl32(cw.h, Wk["out"].h, dst.ctypes.data_as(C.c_void_p), C.c_longlong(cp * NPX), 1)))):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            probe[label + "_ms"] = 1e3 * (time.perf_counter() - t0) / 3
+        ok_xyz = np.array_equal(dst[0]["rgba"], ref0["rgba"]) and (dst[0]["w"] == 1.0).all()
+        probe["xyz_paths_keep_colours"] = bool(ok_xyz)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the timed regions (device-resident and e2e)
+    pcie_rank, pcie_agg = pcie_ceiling(torch, dist, world)
+    for leg in (e2e16, e2e32):
+        bps = max(leg["h2d_bytes_per_step"], leg["d2h_bytes_per_step"]) * world / (leg["ms_per_step"] / 1e3) / 1e9
+        leg["pcie"] = {"busier_direction_GBps_all_ranks": bps, "measured_ceiling_GBps_all_ranks_concurrent": pcie_agg,
+                       "frac_of_ceiling": bps / pcie_agg if pcie_agg > 0 else None}
+    if a.e2e_trace and trace:
+        tz = min(t[4] for t in trace)
+        for t in sorted(trace, key=lambda t: t[4]):
+            sys.stderr.write("%s ctx %d step %d chunk %d: wait_h2d %.2f upload %.2f compute %.2f wait_d2h %.2f download %.2f  [start %.2f end %.2f ms]\n" % (
+                t[0], t[1], t[2], t[3], 1e3 * (t[5] - t[4]), 1e3 * (t[6] - t[5]), 1e3 * (t[7] - t[6]), 1e3 * (t[8] - t[7]),
+                1e3 * (t[9] - t[8]), 1e3 * (t[4] - tz), 1e3 * (t[9] - tz)))
 
     # ---- roofline of the dominant kernel, from per-launch CUDA events in one extra profiled step
     ctx.profile_reset()
@@ -437,37 +752,26 @@ def main():
                 "avg_launch_us": 1e3 * ki["ms"] / max(ki["launches"], 1), "launches_per_step": ki["launches"],
                 "share_of_step": ki["ms"] / ms_prof if ms_prof > 0 else None,
                 "units": "source points x executed iterations (32 B each: 16 R source + 16 R matched target)",
-                "note": "persistent kernel: the target grid lives in shared memory and the working cloud in L2, so DRAM traffic "
-                        "is ~2 % of the algorithmic bytes; the kernel is bound by the serial chain of one ICP iteration (stream, "
-                        "re-query, reduce, cluster exchange, solve) on the slowest pair of the batch, not by HBM (SURVEY H3). "
-                        "The HBM-bound regime (one 25 M-point pair, k_icp_stream: 4.5 TB/s of DRAM traffic, 27 % in algorithmic "
-                        "bytes) is in profiles/r01_final_summary.md"}
+                "note": "persistent kernel, one timed span = the side-by-side launches (one per cluster size) that run the coarse AND "
+                        "the fine align of every pair: the target grid lives in shared memory and the source slice in registers, "
+                        "so DRAM traffic is a few percent of the algorithmic bytes; the kernel is bound by the serial chain of one ICP "
+                        "iteration (cache test, re-query, reduce, cluster exchange, solve) on the slowest pair, not by HBM (SURVEY "
+                        "H3).  The HBM-bound regime (one 50 M-point pair, k_icp_stream) is the point_sharded leg."}
 
     # ---- side measurement (rank 0, N=1): BASELINE configs[2], edge-based NDT on one 1280x720 pair, 0.05 m voxels
     ndt_leg = None
     if rank == 0 and world == 1 and not a.no_ndt:
-        W2, H2 = 1280, 720
-        fr2, T2 = gen_scene.make_sweep(3, 2, W2, H2, noise_scale=0.2)
-        d2 = ctx.upload(list(fr2), W2, H2)
-        v2 = R.voxel_approx(ctx, R.edge_extract(ctx, d2)).download()
-        s2, t2 = ctx.upload([v2[1]]), ctx.upload([v2[0]])
-        p2 = R.ndt_params(resolution=0.05)
-        R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
-        ctx.profile_reset()
-        ctx.profile(True)
-        ctx.timer_start()
-        r2, _ = R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
-        ms2 = ctx.timer_stop()
-        ctx.profile(False)
-        ke, kc = ctx.profile_get("k_ndt_eval"), ctx.profile_get("k_ndt_control")
-        ang2, tr2 = pose_err(r2[0]["T"], gen_scene.pairwise_gt(T2, 1))
-        ndt_leg = {"workload": "configs[2]: edge-based NDT, one 1280x720 pair (921,600 points per frame), 0.05 m voxels, step 0.1, eps 0.01",
-                   "edge_points_src_tgt": [int(len(v2[1])), int(len(v2[0]))], "iterations": r2[0]["iterations"],
-                   "derivative_evals": r2[0]["n_derivative_evals"], "converged": bool(r2[0]["converged"]),
-                   "ms_align": ms2, "ms_per_ndt_iteration": ms2 / max(r2[0]["iterations"], 1),
-                   "ms_per_derivative_eval": ke["ms"] / max(ke["launches"], 1),
-                   "ms_per_control_step": kc["ms"] / max(kc["launches"], 1),
-                   "err_vs_ground_truth_rad_m": [ang2, tr2]}
+        ndt_leg = ndt_config2_leg(ctx, R, gen_scene, guess, peak)
+
+    # ---- side measurement (rank 0, N=1): BASELINE configs[0], the literal rs-pcl --registration path on 3 frames
+    cfg0 = None
+    if rank == 0 and world == 1 and not a.no_configs0:
+        cfg0 = configs0_leg(ctx, R, gen_scene, a)
+
+    # ---- BASELINE configs[4]: one huge pair, source points sharded over the ranks, partial sums all-reduced
+    sharded = None
+    if not a.no_sharded:
+        sharded = point_sharded_leg(ctx, R, gen_scene, torch, dist, rank, world, dev, a, peak)
 
     # ---- CPU baseline (rank 0, N=1 only): oracle, one thread, bounded sample of the same sweep
     cpu = None
@@ -485,21 +789,25 @@ def main():
                "host_threads_available": host_threads()}
 
     if rank == 0:
+        e2e16.update({"pipeline": "%d chunks over %d contexts (streams), pinned host buffers" % (len(chunks), n_ctx), "host_numa": numa,
+                      "note": "host layout = the 16-byte .pcd row (x y z rgb) the reference's --registration mode reads and writes"})
+        e2e32.update({"note": "host layout = pcl::PointXYZRGB in memory (32 B per point, 12 of them padding)",
+                      "download_probe_one_chunk": probe})
         out = {
             "metric": "frame-pair registrations/sec @640x480", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, F),
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": (n_pairs + len(chunks)) * NPX * 32,
-                    "d2h_bytes_per_step": n_pairs * NPX * 32 + n_pairs * 160, "ms_per_step": ms_e2e / a.steps,
-                    "pipeline": "%d chunks over %d contexts (streams), pinned host buffers" % (len(chunks), n_ctx),
-                    "host_numa": numa},
+            "e2e": e2e16,
+            "e2e_pcl32": e2e32,
             "gpu_launches": int(l1 - l0),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernels_ms_per_step": {k: v["ms"] for k, v in kern.items() if v["launches"]},
             "ndt": ndt_leg,
+            "configs0": cfg0,
+            "point_sharded": sharded,
             "ms_per_icp_iteration": (kern[dom]["ms"] + kern["k_icp_solve"]["ms"]) / (2.0 * a.iters if dom == "k_icp_persist" else max(kern[dom]["launches"], 1)),
             "check": {"pairs_converged": n_conv, "max_err_vs_ground_truth": [max_ang, max_tr],
                       "mean_source_edge_points": mean_src},

@@ -79,6 +79,18 @@ int rspcl_cloud_counts(rspcl_ctx* ctx, const rspcl_cloud* c, int32_t* counts);
 int rspcl_cloud_download(rspcl_ctx* ctx, const rspcl_cloud* c, void* host, int layout, long long capacity_points,
                          int32_t* counts);
 
+/* The caller rewrote the colours of an organized batch through its own device code (or wants the gray plane of
+ * edge_extractor.hpp:17-24's Canny input rebuilt): drop the cached (r+g+b)/3 plane; the next edge extraction recomputes it
+ * from the points.  (bench.py uses it to keep the gray conversion INSIDE the timed device-resident step.) */
+int rspcl_cloud_invalidate_gray(rspcl_ctx* ctx, rspcl_cloud* c);
+/* Device -> host of the xyz part only, into a caller buffer that already holds pcl::PointXYZRGB points (32 B each) whose
+ * colours are still valid -- pcl::transformPointCloud(in, out) on out == a copy of in changes 12 of the 32 bytes.  Writes
+ * {x, y, z, 1.0f} (16 B) at a 32-byte pitch and leaves bytes 16..31 of every point untouched.  mode 0: packed staging +
+ * 2-D DMA copy (cudaMemcpy2DAsync); mode 1: a kernel that stores straight into the PINNED host buffer (rspcl_host_alloc)
+ * over PCIe.  Segments are packed back to back like rspcl_cloud_download.  Synchronises. */
+int rspcl_cloud_download_xyz_pcl32(rspcl_ctx* ctx, const rspcl_cloud* c, void* host_pcl32, long long capacity_points,
+                                   int mode);
+
 /* blur_filter.hpp:18-36 BlurFilter::filter (centre 3/5 crop of an organized cloud; also capture.hpp:79-104) */
 int rspcl_crop35(rspcl_ctx* ctx, const rspcl_cloud* in, rspcl_cloud* out);
 
@@ -235,6 +247,22 @@ int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, const int32_
                          int n_pairs, int coarse_kind, const rspcl_icp_params* icp, const rspcl_ndt_params* ndt,
                          const float leaf[3], float t_low, float t_high, const float* guess /* n_pairs x 16 */,
                          rspcl_pair_result* results, rspcl_cloud* out_transformed /* n_pairs segments or NULL */);
+
+/* ------------------------------------------------------------------ sequential registration (the reference's own loop)
+ * TwoPhaseRegistrationScheme::registration (types.hpp:30-43) + ICPEdgeBasedRegistration / NDTEdgeBasedRegistration ::
+ * global_registration (icp:26-130 / ndt:23-117) for ONE sweep, device-resident from the uploaded frames to the merged
+ * cloud: edges of every frame, 1 cm voxel filter, then for k = 1 .. n-1, IN ORDER: coarse stage (ICP or NDT) of frame
+ * k's edges onto the ACCUMULATING edge target from guess[k], fine ICP from identity, and -- if the fine align converged
+ * (icp:113) -- the full frame k moved by both transforms is appended to the merged cloud (icp:120) and the fine-aligned
+ * edges are PREPENDED to the target (icp:119: new points first).  The target lives at the END of its buffer and grows
+ * towards the front, so prepending costs the new points only (no O(total) copy per frame as in `*a = *b + *a`).
+ * frames: organized batch, segment k = frame k.  guess: n x 16 (entry 0 unused) -- R_y(k * rads) for the fixed-angle
+ * schemes (icp:98-100, ndt:86-88).  results: n entries (entry 0: converged = 1, identity transforms).
+ * out_global: 1 segment of stride >= n * w * h.  out_target (optional): 1 segment of stride >= the sum of the voxel-
+ * filtered edge counts -- the final edge target (what icp:126 dumps as dataset/edge_cloud.pcd). */
+int rspcl_register_sequence(rspcl_ctx* ctx, const rspcl_cloud* frames, int coarse_kind, const rspcl_icp_params* icp,
+                            const rspcl_ndt_params* ndt, const float leaf[3], float t_low, float t_high, const float* guess,
+                            rspcl_pair_result* results, rspcl_cloud* out_global, rspcl_cloud* out_target);
 
 #ifdef __cplusplus
 }

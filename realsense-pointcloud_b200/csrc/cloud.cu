@@ -38,17 +38,35 @@ cudaError_t small_d2h(rspcl_ctx* ctx, void* h_dst, const void* d_src, size_t byt
   if (bytes == 0) return cudaSuccess;
   char* slot = (bytes <= (64u << 10) && bytes % 4 == 0 && ((size_t)d_src & 3) == 0) ? z_take(ctx, bytes) : nullptr;
   if (!slot) {
-    // large or odd-sized read-back (masks, index dumps): a pinned, mapped bounce buffer filled by a copy kernel and
-    // copied out at ctx_sync() -- never an asynchronous copy straight into pageable user memory.
+    // large or odd-sized read-back (masks, index dumps, result arrays of big batches): a pinned, mapped staging area
+    // filled by a copy kernel and copied out at ctx_sync() -- never an asynchronous copy straight into pageable user
+    // memory.  The area is persistent and grow-only (a per-call cudaHostAlloc / cudaFreeHost can stall for seconds behind
+    // the driver); only a request that does not fit next to read-backs still pending gets a one-off buffer.
+    const size_t need = (bytes + 255) & ~(size_t)255;
     void* bounce = nullptr;
-    cudaError_t e = cudaHostAlloc(&bounce, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
-    if (e != cudaSuccess) return e;
+    void* owned = nullptr;
+    if (ctx->h_stage_used == 0 && ctx->h_stage_bytes < need) {
+      if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+      ctx->h_stage = nullptr;
+      ctx->h_stage_bytes = 0;
+      const size_t want = need < (8u << 20) ? (8u << 20) : need * 2;
+      if (cudaHostAlloc(&ctx->h_stage, want, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) ctx->h_stage_bytes = want;
+      else cudaGetLastError();
+    }
+    if (ctx->h_stage && ctx->h_stage_used + need <= ctx->h_stage_bytes) {
+      bounce = (char*)ctx->h_stage + ctx->h_stage_used;
+      ctx->h_stage_used += need;
+    } else {
+      cudaError_t e = cudaHostAlloc(&bounce, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+      if (e != cudaSuccess) return e;
+      owned = bounce;
+    }
     if (bytes % 4 == 0 && ((size_t)d_src & 3) == 0)
       k_copy_words<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>((unsigned*)bounce, (const unsigned*)d_src, (int)(bytes / 4));
     else
       k_copy_bytes<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>((unsigned char*)bounce, (const unsigned char*)d_src, bytes);
     ctx->launches++;
-    ctx->z_pending.push_back({h_dst, bounce, bytes, bounce});
+    ctx->z_pending.push_back({h_dst, bounce, bytes, owned});
     return cudaGetLastError();
   }
   const int nw = (int)(bytes / 4);
@@ -66,19 +84,9 @@ cudaError_t ctx_sync(rspcl_ctx* ctx) {
     if (p.owned) cudaFreeHost(p.owned);
   }
   ctx->z_pending.clear();
-  ctx->z_used = 0;  // everything enqueued so far has executed: the arena can be recycled
+  ctx->z_used = 0;  // everything enqueued so far has executed: the arenas can be recycled
+  ctx->h_stage_used = 0;
   return cudaSuccess;
-}
-
-int ensure_stage(rspcl_ctx* ctx, size_t bytes) {
-  if (ctx->h_stage_bytes >= bytes) return RSPCL_OK;
-  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-  ctx->h_stage = nullptr;
-  ctx->h_stage_bytes = 0;
-  size_t want = bytes < 65536 ? 65536 : bytes * 2;
-  CU(ctx, cudaMallocHost(&ctx->h_stage, want));
-  ctx->h_stage_bytes = want;
-  return RSPCL_OK;
 }
 
 extern "C" int rspcl_ctx_create(int device, rspcl_ctx** out) {
@@ -426,6 +434,65 @@ extern "C" int rspcl_cloud_download(rspcl_ctx* ctx, const rspcl_cloud* c, void* 
   CU(ctx, ctx_sync(ctx));
   scratch_free(ctx, d_off);
   scratch_free(ctx, (char*)raw);
+  return RSPCL_OK;
+}
+
+extern "C" int rspcl_cloud_invalidate_gray(rspcl_ctx* ctx, rspcl_cloud* c) {
+  if (!ctx || !c) return RSPCL_ERR_ARG;
+  invalidate_gray(c);
+  return RSPCL_OK;
+}
+
+// xyz1 of every point, packed (16 B per point) or straight into a 32-byte-pitch host buffer
+__global__ void k_pack_xyz1(const float4* __restrict__ pts, const int* __restrict__ offsets, const int* __restrict__ count,
+                            float4* __restrict__ out, int stride, int out_pitch_f4) {
+  const int seg = blockIdx.y;
+  const int n = count[seg];
+  const long long base = offsets[seg];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[(size_t)seg * stride + i];
+    p.w = 1.0f;
+    out[(size_t)(base + i) * out_pitch_f4] = p;
+  }
+}
+
+extern "C" int rspcl_cloud_download_xyz_pcl32(rspcl_ctx* ctx, const rspcl_cloud* c, void* host, long long capacity_points,
+                                              int mode) {
+  if (!ctx || !c || !host || (mode != 0 && mode != 1)) return RSPCL_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  std::vector<int> cnt(c->n_seg);
+  int rc = rspcl_cloud_counts(ctx, c, cnt.data());
+  if (rc) return rc;
+  std::vector<int> off(c->n_seg + 1);
+  long long total = 0;
+  int maxc = 0;
+  for (int s = 0; s < c->n_seg; ++s) {
+    off[s] = (int)total;
+    total += cnt[s];
+    maxc = cnt[s] > maxc ? cnt[s] : maxc;
+  }
+  off[c->n_seg] = (int)total;
+  if (total > capacity_points) RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "download_xyz: %lld points, capacity %lld", total, capacity_points);
+  if (total == 0) return RSPCL_OK;
+  Scratch scr(ctx);
+  int* d_off = nullptr;
+  CU(ctx, scr.alloc(&d_off, (size_t)c->n_seg + 1));
+  CU(ctx, small_h2d(ctx, d_off, off.data(), (c->n_seg + 1) * sizeof(int)));
+  dim3 grid(blocks_per_seg(ctx, c->n_seg, maxc, 256), c->n_seg);
+  if (mode == 0) {
+    float4* raw = nullptr;
+    CU(ctx, scr.alloc(&raw, (size_t)total));
+    k_pack_xyz1<<<grid, 256, 0, ctx->stream>>>(c->pts, d_off, c->count, raw, c->stride, 1);
+    LAUNCH_CHECK(ctx);
+    CU(ctx, cudaMemcpy2DAsync(host, 32, raw, 16, 16, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    void* dev_view = nullptr;  // the pinned buffer as the device sees it (identical under unified addressing)
+    CU(ctx, cudaHostGetDevicePointer(&dev_view, host, 0));
+    k_pack_xyz1<<<grid, 256, 0, ctx->stream>>>(c->pts, d_off, c->count, (float4*)dev_view, c->stride, 2);
+    LAUNCH_CHECK(ctx);
+  }
+  CU(ctx, ctx_sync(ctx));
+  scr.ok();
   return RSPCL_OK;
 }
 

@@ -7,6 +7,7 @@
 // the system library), so the library has no hard dependency on it: single-GPU users never touch it.
 #include "common.cuh"
 #include <dlfcn.h>
+#include <stdlib.h>
 
 namespace {
 typedef struct { char internal[128]; } NcclUniqueId;
@@ -15,6 +16,7 @@ typedef int (*fn_get_unique_id)(NcclUniqueId*);
 typedef int (*fn_comm_init_rank)(NcclComm*, int, NcclUniqueId, int);
 typedef int (*fn_comm_destroy)(NcclComm);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_all_gather)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
 typedef const char* (*fn_get_error_string)(int);
 
 struct NcclApi {
@@ -23,6 +25,7 @@ struct NcclApi {
   fn_comm_init_rank comm_init_rank = nullptr;
   fn_comm_destroy comm_destroy = nullptr;
   fn_all_reduce all_reduce = nullptr;
+  fn_all_gather all_gather = nullptr;
   fn_get_error_string get_error_string = nullptr;
 };
 
@@ -37,6 +40,7 @@ NcclApi* nccl() {
       api.comm_init_rank = (fn_comm_init_rank)dlsym(api.lib, "ncclCommInitRank");
       api.comm_destroy = (fn_comm_destroy)dlsym(api.lib, "ncclCommDestroy");
       api.all_reduce = (fn_all_reduce)dlsym(api.lib, "ncclAllReduce");
+      api.all_gather = (fn_all_gather)dlsym(api.lib, "ncclAllGather");
       api.get_error_string = (fn_get_error_string)dlsym(api.lib, "ncclGetErrorString");
     }
   }
@@ -44,6 +48,95 @@ NcclApi* nccl() {
   return &api;
 }
 }  // namespace
+
+// Peer-memory exchange buffers: every rank allocates [2 parities][nranks][PX_WORDS] doubles + flags, exports the
+// allocation through CUDA IPC, the handles travel through one ncclAllGather, and every rank maps every peer's buffer
+// (NVLink P2P on an NVSwitch box).  RSPCL_PEER_XCHG=0 keeps the ncclAllReduce path.
+static size_t px_bytes(int nranks) {
+  return ((size_t)2 * nranks * PX_WORDS + (size_t)2 * nranks * PX_MAXPAIRS) * 8;
+}
+
+static void peer_teardown(rspcl_ctx* ctx) {
+  for (int r = 0; r < PX_MAXRANKS; ++r) {
+    if (ctx->px_peer[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->px_peer[r]);
+    ctx->px_peer[r] = nullptr;
+  }
+  if (ctx->px_local) cudaFree(ctx->px_local);
+  if (ctx->px_err) cudaFree(ctx->px_err);
+  ctx->px_local = nullptr;
+  ctx->px_err = nullptr;
+  ctx->px_seq = 0;
+  cudaGetLastError();
+}
+
+static void peer_setup(rspcl_ctx* ctx, NcclApi* a) {
+  const char* env = getenv("RSPCL_PEER_XCHG");
+  if ((env && env[0] == '0') || ctx->nranks < 2 || ctx->nranks > PX_MAXRANKS || !a->all_gather) return;
+  const size_t bytes = px_bytes(ctx->nranks);
+  cudaIpcMemHandle_t mine;
+  char* d_handles = nullptr;
+  bool ok = cudaMalloc(&ctx->px_local, bytes) == cudaSuccess && cudaMemset(ctx->px_local, 0, bytes) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->px_err, sizeof(int)) == cudaSuccess && cudaMemset(ctx->px_err, 0, sizeof(int)) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine, ctx->px_local) == cudaSuccess &&
+            cudaMalloc((void**)&d_handles, (size_t)ctx->nranks * sizeof(mine)) == cudaSuccess;
+  std::vector<cudaIpcMemHandle_t> all(ctx->nranks);
+  if (ok) {
+    ok = cudaMemcpy(d_handles + (size_t)ctx->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess &&
+         a->all_gather(d_handles + (size_t)ctx->rank * sizeof(mine), d_handles, sizeof(mine), /*ncclInt8*/ 0, (NcclComm)ctx->nccl_comm,
+                       ctx->stream) == 0 &&
+         cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+         cudaMemcpy(all.data(), d_handles, (size_t)ctx->nranks * sizeof(mine), cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  // every rank must take the same decision: a rank whose setup failed still went through the all-gather above when it
+  // could; the final agreement is one more tiny all-reduce of the ok flags
+  for (int r = 0; ok && r < ctx->nranks; ++r) {
+    if (r == ctx->rank) {
+      ctx->px_peer[r] = ctx->px_local;
+    } else if (cudaIpcOpenMemHandle(&ctx->px_peer[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ctx->px_peer[r] = nullptr;
+      ok = false;
+    }
+  }
+  if (d_handles) cudaFree(d_handles);
+  double flag = ok ? 0.0 : 1.0, *d_flag = nullptr;
+  if (cudaMalloc((void**)&d_flag, sizeof(double)) == cudaSuccess) {
+    cudaMemcpy(d_flag, &flag, sizeof(double), cudaMemcpyHostToDevice);
+    if (a->all_reduce(d_flag, d_flag, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, (NcclComm)ctx->nccl_comm, ctx->stream) == 0 &&
+        cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+      cudaMemcpy(&flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost);
+    else
+      flag = 1.0;
+    cudaFree(d_flag);
+  } else {
+    flag = 1.0;
+  }
+  cudaGetLastError();
+  if (flag != 0.0) peer_teardown(ctx);  // somebody could not map a peer: everybody stays on NCCL
+}
+
+bool comm_peer_ready(const rspcl_ctx* ctx, int n_pairs, int vals_per_pair) {
+  const char* env = getenv("RSPCL_PEER_XCHG");  // "0": keep ncclAllReduce for this call (must be set on every rank alike)
+  if (env && env[0] == '0') return false;
+  return ctx->px_local != nullptr && ctx->nranks > 1 && n_pairs <= PX_MAXPAIRS && (long long)n_pairs * vals_per_pair <= PX_WORDS;
+}
+
+PeerX comm_peer_next(rspcl_ctx* ctx) {
+  PeerX X;
+  for (int r = 0; r < PX_MAXRANKS; ++r) X.peer[r] = (double*)ctx->px_peer[r];
+  X.nranks = ctx->nranks;
+  X.rank = ctx->rank;
+  X.seq = ctx->px_seq++;
+  X.err = ctx->px_err;
+  return X;
+}
+
+int comm_peer_check(rspcl_ctx* ctx) {
+  if (!ctx->px_err) return RSPCL_OK;
+  int e = 0;
+  CU(ctx, cudaMemcpy(&e, ctx->px_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) RSPCL_FAIL(ctx, RSPCL_ERR_CUDA, "point-sharded exchange timed out: a rank did not reach the collective");
+  return RSPCL_OK;
+}
 
 extern "C" int rspcl_comm_unique_id(void* id128) {
   NcclApi* a = nccl();
@@ -67,6 +160,7 @@ extern "C" int rspcl_comm_init(rspcl_ctx* ctx, int nranks, int rank, const void*
   ctx->nccl_comm = comm;
   ctx->nranks = nranks;
   ctx->rank = rank;
+  peer_setup(ctx, a);  // best effort: without it the partial sums go through ncclAllReduce
   return RSPCL_OK;
 }
 
@@ -75,6 +169,7 @@ extern "C" int rspcl_comm_destroy(rspcl_ctx* ctx) {
   NcclApi* a = nccl();
   if (a && ctx->nccl_comm) {
     cudaStreamSynchronize(ctx->stream);
+    peer_teardown(ctx);
     a->comm_destroy((NcclComm)ctx->nccl_comm);
   }
   ctx->nccl_comm = nullptr;

@@ -21,7 +21,7 @@ struct rspcl_ctx {
   int sm_count = 148;
   // grow-only pinned staging buffer for small result read-backs
   void* h_stage = nullptr;
-  size_t h_stage_bytes = 0;
+  size_t h_stage_bytes = 0, h_stage_used = 0;
   // Zero-copy control channel: small host<->device transfers (counts, indices, 4x4 matrices, convergence states) go
   // through a mapped pinned arena read/written by tiny kernels, so they never queue behind another context's bulk DMA
   // on the copy engines.  Device->host items are copied out of the arena at the next ctx_sync().
@@ -37,6 +37,12 @@ struct rspcl_ctx {
   // point-sharded mode (comm.cu)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // one-shot peer-memory exchange of the per-iteration partial sums (comm.cu): every rank's buffer mapped into every
+  // other rank through CUDA IPC over NVLink; falls back to ncclAllReduce when the mapping could not be set up
+  void* px_local = nullptr;
+  void* px_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* px_err = nullptr;            // device flag: an exchange timed out
+  unsigned long long px_seq = 0;    // exchanges issued so far (identical on every rank: the calls are collective)
   bool sharded_call = false;  // set for the duration of a *_sharded entry point
   // optional per-kernel event profile
   bool prof_on = false;
@@ -128,11 +134,58 @@ static inline void scratch_free(rspcl_ctx* ctx, T* p) {
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-int ensure_stage(rspcl_ctx* ctx, size_t bytes);
 cudaError_t small_h2d(rspcl_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 cudaError_t small_d2h(rspcl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);  // valid after ctx_sync()
 cudaError_t ctx_sync(rspcl_ctx* ctx);
 int comm_allreduce_f64(rspcl_ctx* ctx, double* buf, size_t n);
+
+// ---- one-shot all-reduce of a few doubles per pair through peer memory (point-sharded mode)
+constexpr int PX_MAXRANKS = 8;
+constexpr int PX_WORDS = 8192;   // doubles per (parity, source rank) slot
+constexpr int PX_MAXPAIRS = 256; // flag slots per (parity, source rank)
+struct PeerX {                   // passed by value to the kernels that exchange
+  double* peer[PX_MAXRANKS];     // rank r's buffer as THIS rank sees it (peer[rank] = the local buffer)
+  int nranks, rank;
+  unsigned long long seq;        // index of this exchange
+  int* err;
+};
+bool comm_peer_ready(const rspcl_ctx* ctx, int n_pairs, int vals_per_pair);
+PeerX comm_peer_next(rspcl_ctx* ctx);   // descriptor of the next exchange (advances the sequence number)
+int comm_peer_check(rspcl_ctx* ctx);    // after a sync: did any exchange time out?
+
+// Called by one whole warp per pair: lane k < n_vals contributes v; returns the sum over the ranks of value k (in rank
+// order, so every rank gets the same bits).  Data first, then a system-scope fence, then one flag per destination; the
+// receiver spins on its LOCAL flags (bounded: a missing peer sets *err instead of hanging the GPU).
+static __device__ __forceinline__ double peer_allreduce_warp(const PeerX& X, double v, int lane, int n_vals, int pair) {
+  const int par = (int)(X.seq & 1ull);
+  const size_t flags_off = (size_t)2 * X.nranks * PX_WORDS;  // in 8-byte words
+  if (lane < n_vals)
+    for (int r = 0; r < X.nranks; ++r) X.peer[r][((size_t)par * X.nranks + X.rank) * PX_WORDS + (size_t)pair * n_vals + lane] = v;
+  __threadfence_system();
+  __syncwarp();
+  if (lane < X.nranks) {
+    volatile unsigned long long* f =
+        reinterpret_cast<volatile unsigned long long*>(X.peer[lane] + flags_off) + ((size_t)par * X.nranks + X.rank) * PX_MAXPAIRS + pair;
+    *f = X.seq + 1;  // (st.volatile to peer memory after the fence: the data is visible before the flag)
+    volatile unsigned long long* mine =
+        reinterpret_cast<volatile unsigned long long*>(X.peer[X.rank] + flags_off) + ((size_t)par * X.nranks + lane) * PX_MAXPAIRS + pair;
+    const long long t0 = clock64();
+    while (*mine < X.seq + 1) {
+      if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
+        *X.err = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+  double out = 0.0;
+  if (lane < n_vals) {
+    const volatile double* L = X.peer[X.rank];
+    for (int r = 0; r < X.nranks; ++r) out += L[((size_t)par * X.nranks + r) * PX_WORDS + (size_t)pair * n_vals + lane];
+  }
+  return out;
+}
 // Options of the device-level ICP align (icp.cu)
 struct IcpAlignOpts {
   int* d_corr_out = nullptr;                 // device correspondence dump [iteration][pair][stride] (match index or -1)
@@ -165,6 +218,7 @@ struct Scratch {
         if (q.owned) cudaFreeHost(q.owned);
       ctx->z_pending.clear();
       ctx->z_used = 0;
+      ctx->h_stage_used = 0;
       cudaGetLastError();
     }
     for (void* q : ptrs) cudaFreeAsync(q, ctx->stream);
@@ -231,6 +285,41 @@ __device__ __forceinline__ float dist2_l2simple(float ax, float ay, float az, fl
   r = fadd(r, fmul(d, d));
   return r;
 }
+
+// ---- shared-memory / cluster PTX helpers
+static __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 8-byte store into a (possibly remote) CTA of the cluster that completes 8 transaction bytes on that CTA's mbarrier:
+// data and signal travel together, no fence and no cluster-wide barrier
+static __device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_mbar)
+               : "memory");
+}
+static __device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned addr, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void mbar_wait_cluster(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

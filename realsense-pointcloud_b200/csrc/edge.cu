@@ -34,7 +34,8 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // discretizeAngles on atan2f(gy,gx) * 57.29578f.  The angle is evaluated in double and rounded to float, which
 // reproduces a correctly rounded atan2f except within ~1e-9 relative of a rounding boundary; the oracle counts pixels
 // whose angle sits within 1e-3 degrees of a bin threshold (near_bin_edge) so a disagreement would be visible.
-__device__ __forceinline__ int direction_bin(float gy, float gx) {
+// (Slow path: only gradients within 1e-5 relative of a bin boundary get here, see direction_bin_fast.)
+__device__ __noinline__ int direction_bin(float gy, float gx) {
   float rad = (float)atan2((double)gy, (double)gx);
   float angle = fmul(rad, 57.29578f);
   if (((angle <= 22.5f) && (angle >= -22.5f)) || (angle >= 157.5f) || (angle <= -157.5f)) return 0;
@@ -42,6 +43,19 @@ __device__ __forceinline__ int direction_bin(float gy, float gx) {
   if (((angle >= 67.5f) && (angle <= 112.5f)) || ((angle <= -67.5f) && (angle >= -112.5f))) return 90;
   if (((angle > 112.5f) && (angle < 157.5f)) || ((angle < -22.5f) && (angle > -67.5f))) return 135;
   return 255;
+}
+
+// The same bins from comparisons: the four thresholds +-22.5 / +-67.5 / +-112.5 / +-157.5 degrees are the lines
+// |gy| = tan(22.5 deg) |gx| and |gy| = tan(67.5 deg) |gx|, and the diagonal bins differ by the sign of gy * gx.  A
+// gradient within 1e-5 (relative) of a boundary -- where the rounding of atan2f and of the degree conversion, and the
+// <= / < conventions of discretizeAngles, decide -- takes the atan2 path, so the result is the oracle's bin always.
+__device__ __forceinline__ int direction_bin_fast(float gy, float gx) {
+  const float a = fabsf(gy), b = fabsf(gx);
+  const float l1 = 0.41421356f * b, l2 = 2.41421356f * b;
+  if (fabsf(a - l1) <= 1e-5f * (a + l1) || fabsf(a - l2) <= 1e-5f * (a + l2)) return direction_bin(gy, gx);
+  if (a < l1) return 0;
+  if (a > l2) return 90;
+  return ((gy > 0.f) == (gx > 0.f)) ? 45 : 135;
 }
 
 // ---- lock-free union-find over candidate pixels (per frame; parents are pixel indices within the frame)
@@ -76,6 +90,7 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
   __shared__ float s_gray[GH][GW + 1];
   __shared__ float s_blur[BH][BW + 1];
   __shared__ float s_mag[MH][MW + 1];
+  __shared__ uint8_t s_dir[TH][TW];  // direction bin of the centre pixels that can survive (magnitude >= t_low), else 255
   __shared__ uint8_t s_cls[TH][TW];
   __shared__ int s_par[TH * TW];  // tile-local union-find (parents are local pixel indices i * TW + j)
   const int seg = blockIdx.z;
@@ -83,11 +98,28 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const uint8_t* g = gray + (size_t)seg * stride;
 
-  // 1. gray tile with replicate borders (Convolution BOUNDARY_OPTION_CLAMP)
-  for (int k = tid; k < GH * GW; k += 256) {
-    int i = k / GW, j = k % GW;
-    int r = clampi(r0 - 3 + i, 0, h - 1), c = clampi(c0 - 3 + j, 0, w - 1);
-    s_gray[i][j] = (float)g[(size_t)r * w + c];
+  // 1. gray tile with replicate borders (Convolution BOUNDARY_OPTION_CLAMP).  Tiles whose halo lies inside the row (all
+  //    but the first / last tile column) and whose rows are 16-byte aligned take 128-bit loads: the GW = 70 bytes of a
+  //    tile row sit inside six aligned 16-byte words starting 16 bytes left of the tile.
+  const bool vec_ok = (w % 16 == 0) && (stride % 16 == 0) && c0 >= 16 && c0 + TW + 16 <= w;
+  if (vec_ok) {
+    for (int k = tid; k < GH * 6; k += 256) {
+      const int i = k / 6, q = k % 6;
+      const int r = clampi(r0 - 3 + i, 0, h - 1);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * w + (c0 - 16)) + q);
+      const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int j = 16 * q - 13 + t;  // tile column of byte t of word q (tile column 0 = image column c0 - 3)
+        if (j >= 0 && j < GW) s_gray[i][j] = (float)((wd[t >> 2] >> (8 * (t & 3))) & 255u);
+      }
+    }
+  } else {
+    for (int k = tid; k < GH * GW; k += 256) {
+      int i = k / GW, j = k % GW;
+      int r = clampi(r0 - 3 + i, 0, h - 1), c = clampi(c0 - 3 + j, 0, w - 1);
+      s_gray[i][j] = (float)g[(size_t)r * w + c];
+    }
   }
   __syncthreads();
   // 2. blur evaluated AT THE CLAMPED COORDINATE of every halo-2 position (what the Sobel pass will read)
@@ -131,6 +163,10 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
           gy = fadd(gy, fmul(sy[kr * 3 + kc], v));
         }
       m = __fsqrt_rn(fadd(fmul(gx, gx), fmul(gy, gy)));
+      // the direction is only ever read for centre pixels that pass the low threshold (suppressNonMaxima)
+      if (i >= 1 && i <= TH && j >= 1 && j <= TW) s_dir[i - 1][j - 1] = !(m < t_low) ? (uint8_t)direction_bin_fast(gy, gx) : (uint8_t)255;
+    } else if (i >= 1 && i <= TH && j >= 1 && j <= TW) {
+      s_dir[i - 1][j - 1] = 255;
     }
     s_mag[i][j] = m;
   }
@@ -144,25 +180,7 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
     if (r >= 1 && r < h - 1 && c >= 1 && c < w - 1) {
       float m = s_mag[i + 1][j + 1];
       if (!(m < t_low)) {
-        // recompute the gradient of this pixel for its direction (cheaper than a second smem plane)
-        int bi[3], bj[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          bi[d] = (r + d - 1) - (r0 - 2);
-          bj[d] = (c + d - 1) - (c0 - 2);
-        }
-        const float sx[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};
-        const float sy[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};
-        float gx = 0.f, gy = 0.f;
-#pragma unroll
-        for (int kr = 0; kr < 3; ++kr)
-#pragma unroll
-          for (int kc = 0; kc < 3; ++kc) {
-            float v = s_blur[bi[kr]][bj[kc]];
-            gx = fadd(gx, fmul(sx[kr * 3 + kc], v));
-            gy = fadd(gy, fmul(sy[kr * 3 + kc], v));
-          }
-        int dir = direction_bin(gy, gx);
+        const int dir = s_dir[i][j];
         float a = 0.f, b = 0.f;
         bool ok = true;
         switch (dir) {

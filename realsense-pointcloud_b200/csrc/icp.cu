@@ -608,6 +608,27 @@ __global__ void __launch_bounds__(32) k_icp_solve(IcpState* __restrict__ st, con
   icp_solve_pair(&st[seg], sums, prm, n_active, lane);
 }
 
+// point-sharded mode, peer-memory path: the same warp combines this rank's CTA partials, exchanges the 17 totals with every
+// other rank through NVLink peer memory (one-shot all-reduce, comm.cu / common.cuh) and runs the solve -- one launch instead
+// of {sum partials, ncclAllReduce, solve}.  Every rank sums the ranks' totals in rank order: identical bits, identical
+// convergence decisions, no broadcast.
+__global__ void __launch_bounds__(32) k_icp_solve_peer(IcpState* __restrict__ st, const double* __restrict__ partials, int nblk,
+                                                       IcpDevParams prm, int* __restrict__ n_active, PeerX X) {
+  const int seg = blockIdx.x;
+  if (st[seg].done) return;  // (identical on every rank)
+  const int lane = threadIdx.x;
+  __shared__ double sums[NRED];
+  double v = 0;
+  if (lane < NRED) {
+    const double* P = partials + (size_t)seg * nblk * NRED + lane;
+    for (int b = 0; b < nblk; ++b) v += P[(size_t)b * NRED];
+  }
+  v = peer_allreduce_warp(X, v, lane, NRED, seg);
+  if (lane < NRED) sums[lane] = v;
+  __syncwarp();
+  icp_solve_pair(&st[seg], sums, prm, n_active, lane);
+}
+
 __global__ void k_copy_work(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
                             float4* __restrict__ work, int stride_work) {
   const int seg = blockIdx.y;
@@ -1174,19 +1195,59 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     // a batch planned for all 148 SMs left a few clusters waiting for a second wave, +20 % launch time)
     double budget = ctx->sm_count - 2;
     if (const char* e = getenv("RSPCL_PERSIST_BUDGET")) budget = atof(e) > 0 ? atof(e) : budget;  // tuning knob
-    plan_clusters(hcnt, budget, ctx->cluster_weight, &cl);
-    std::vector<int> order;
-    int goff[P_CLMAX + 1], max_cl = 1;  // group gi holds the pairs with clusters of P_CLMAX - gi CTAs (largest first)
-    for (int gi = 0; gi < P_CLMAX; ++gi) {
-      goff[gi] = (int)order.size();
-      std::vector<int> grp;
-      for (int s = 0; s < S; ++s)
-        if (cl[s] == P_CLMAX - gi && !(o.h_skip && o.h_skip[s])) grp.push_back(s);
-      std::stable_sort(grp.begin(), grp.end(), [&](int a, int b) { return hcnt[a] > hcnt[b]; });
-      order.insert(order.end(), grp.begin(), grp.end());
-      if (!grp.empty() && P_CLMAX - gi > max_cl) max_cl = P_CLMAX - gi;
+    // Waves.  A batch that fits the chip -- or whose pairs all fit one CTA's registers, so that the hardware can simply
+    // stream single-CTA clusters through the SMs -- is one wave.  A larger batch of larger pairs (e.g. 4096 frame pairs
+    // of ~7 k points) is cut, in decreasing size, into waves that each fill the chip with register-resident slices.
+    cl.assign(S, 1);
+    std::vector<int> todo;
+    int max_cnt = 0;
+    for (int s = 0; s < S; ++s)
+      if (!(o.h_skip && o.h_skip[s])) {
+        todo.push_back(s);
+        max_cnt = hcnt[s] > max_cnt ? hcnt[s] : max_cnt;
+      }
+    std::stable_sort(todo.begin(), todo.end(), [&](int a, int b) { return hcnt[a] > hcnt[b]; });
+    std::vector<std::vector<int>> waves;
+    if ((int)todo.size() <= (int)budget || max_cnt <= P_CHUNK) {
+      waves.push_back(todo);
+    } else {
+      double need = 0;
+      std::vector<int> cur;
+      for (int s : todo) {
+        int cmin = (hcnt[s] + P_CHUNK - 1) / P_CHUNK;
+        cmin = cmin < 1 ? 1 : (cmin > P_CLMAX ? P_CLMAX : cmin);
+        const double w = ctx->cluster_weight[cmin];
+        if (!cur.empty() && need + w > budget) {
+          waves.push_back(cur);
+          cur.clear();
+          need = 0;
+        }
+        cur.push_back(s);
+        need += w;
+      }
+      if (!cur.empty()) waves.push_back(cur);
     }
-    goff[P_CLMAX] = (int)order.size();
+    // launch groups: per wave, per cluster size (largest first), pairs in decreasing size
+    struct Group { int off, n, cl, wave; };
+    std::vector<Group> groups;
+    std::vector<int> order;
+    int max_cl = 1;
+    for (size_t wv = 0; wv < waves.size(); ++wv) {
+      std::vector<int> wc(waves[wv].size()), wcl;
+      for (size_t k = 0; k < wc.size(); ++k) wc[k] = hcnt[waves[wv][k]];
+      plan_clusters(wc, budget, ctx->cluster_weight, &wcl);
+      for (size_t k = 0; k < wc.size(); ++k) cl[waves[wv][k]] = wcl[k];
+      for (int c = P_CLMAX; c >= 1; --c) {
+        Group g{(int)order.size(), 0, c, (int)wv};
+        for (int s : waves[wv])  // (already in decreasing size)
+          if (cl[s] == c) order.push_back(s);
+        g.n = (int)order.size() - g.off;
+        if (g.n > 0) {
+          groups.push_back(g);
+          max_cl = c > max_cl ? c : max_cl;
+        }
+      }
+    }
     int* d_order = nullptr;
     unsigned short* d_tidx = nullptr;  // original index of every cell-sorted target point (tie-breaks, correspondences)
     float* d_lb = nullptr;             // streamed slices only: certified bounds between iterations
@@ -1213,6 +1274,15 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     pa.st1 = st;
     pa.st2 = st2;
     pa.n_stages = two_stage ? 2 : 1;
+    pa.prev2 = nullptr;
+    if (two_stage) {
+      double* d_prev2 = nullptr;
+      std::vector<double> p2(S);
+      for (int s = 0; s < S; ++s) p2[s] = o.h_results2[s].prev_mse;
+      CU(ctx, scr.alloc(&d_prev2, (size_t)S));
+      CU(ctx, small_h2d(ctx, d_prev2, p2.data(), S * sizeof(double)));
+      pa.prev2 = d_prev2;
+    }
     pa.tgt = tgt->pts;
     pa.tcount = tgt->count;
     pa.tstride = tgt->stride;
@@ -1229,16 +1299,17 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     pa.dbg_iter = d_dbg_iter;
     {
       ProfScope prof(ctx, "k_icp_persist", 0.0);
-      // one launch per cluster size; the launches of a batch run side by side (largest clusters first: they are the
-      // hardest to place) on the context stream and forked streams
-      int n_groups = 0;
-      for (int gi = 0; gi < P_CLMAX; ++gi) n_groups += goff[gi + 1] > goff[gi] ? 1 : 0;
-      if (n_groups > 1) CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-      int used = 0;
-      for (int gi = 0; gi < P_CLMAX; ++gi) {
-        const int ng = goff[gi + 1] - goff[gi];
-        if (ng <= 0) continue;
-        const int gcl_i = P_CLMAX - gi;
+      // one launch per cluster size; the launches of a wave run side by side (largest clusters first: they are the
+      // hardest to place) on the context stream and forked streams, waves follow one another
+      int used = 0, cur_wave = -1;
+      for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const int ng = groups[gi].n, gcl_i = groups[gi].cl;
+        if (groups[gi].wave != cur_wave) {  // new wave: everything forked so far has been joined into the context stream
+          cur_wave = groups[gi].wave;
+          used = 0;
+          const bool forks = gi + 1 < groups.size() && groups[gi + 1].wave == cur_wave;
+          if (forks) CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        }
         cudaStream_t strm = used == 0 ? ctx->stream : ctx->aux[used - 1];
         if (used > 0) CU(ctx, cudaStreamWaitEvent(strm, ctx->ev_fork, 0));
         cudaLaunchConfig_t cfg = {};
@@ -1254,7 +1325,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         cfg.attrs = at;
         cfg.numAttrs = 1;
         PersistArgs pg = pa;
-        pg.order = d_order + goff[gi];
+        pg.order = d_order + groups[gi].off;
         CU(ctx, cudaLaunchKernelEx(&cfg, persist_fn(want_dbg), pg, dp));
         LAUNCH_CHECK(ctx);
         if (used > 0) {
@@ -1381,11 +1452,18 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         LAUNCH_CHECK(ctx);
       }
       ProfScope prof2(ctx, "k_icp_solve", (double)S);
-      if (sharded) {
-        // partial sums of this rank's shard -> all-reduce over NVLink -> identical solve on every rank
+      if (sharded && comm_peer_ready(ctx, S, NRED)) {
+        // partial sums of this rank's shard -> one-shot exchange through peer memory, fused with the solve
+        k_icp_solve_peer<<<S, 32, 0, ctx->stream>>>(st, partials, nblk_total, dp, n_active, comm_peer_next(ctx));
+      } else if (sharded) {
+        // partial sums of this rank's shard -> ncclAllReduce -> identical solve on every rank
         k_icp_sum_partials<<<S, 32, 0, ctx->stream>>>(partials, nblk_total, st, totals);
         LAUNCH_CHECK(ctx);
-        int rcc = comm_allreduce_f64(ctx, totals, (size_t)S * NRED);
+        int rcc;
+        {
+          ProfScope prof_ar(ctx, "allreduce", (double)S * NRED * sizeof(double));
+          rcc = comm_allreduce_f64(ctx, totals, (size_t)S * NRED);
+        }
         if (rcc) return rcc;
         k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, totals, 1, dp, n_active);
       } else {
@@ -1429,6 +1507,10 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   }
   CU(ctx, ctx_sync(ctx));
   if (rc) return rc;
+  if (sharded) {
+    rc = comm_peer_check(ctx);
+    if (rc) return rc;
+  }
   if (range) RSPCL_FAIL(ctx, RSPCL_ERR_RANGE, "icp_align: target coordinates exceed the grid key range (+-32767 cells of %g m)", cs);
   auto put = [](rspcl_icp_result& r, const IcpState& h) {
     memcpy(r.T, h.final_T, sizeof(float) * 16);

@@ -140,6 +140,7 @@ struct PersistArgs {
   IcpState* st1;            // in: state initialised by k_icp_init (guess); out: result of the (coarse) align
   IcpState* st2;            // out: result of the second (fine) align, run from identity on the source moved by the first
   int n_stages;             // 1 or 2
+  const double* prev2;      // second align: correspondences_prev_mse_ of its PCL object on entry (null: DBL_MAX, a fresh object)
   const float4* tgt;
   const int* tcount;
   int tstride;
@@ -156,40 +157,6 @@ struct PersistArgs {
   long long* dbg_iter;      // optional per-iteration trace of the launch's first CTA: {re-queried points, phase-B cycles, iteration cycles}
 };
 
-
-// ---- shared-memory / cluster PTX helpers
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
-  unsigned r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-// 8-byte store into a (possibly remote) CTA of the cluster that completes 8 transaction bytes on that CTA's mbarrier:
-// data and signal travel together, no fence and no cluster-wide barrier
-__device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
-               "l"(__double_as_longlong(v)), "r"(remote_mbar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned addr, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(unsigned addr, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(addr),
-      "r"(parity)
-      : "memory");
-}
 
 // One pass of exact re-queries over the work list: G lanes per item.
 //   G = 4: every lane probes two of the (<= 8) neighbour cells, then the four lanes walk all occupied cells together,
@@ -804,7 +771,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_icp_persist(const PersistArgs 
       if (tid == 0) {
         mat4_identity(S.st.final_T);
         mat4_identity(S.st.inc_T);
-        S.st.prev_mse = DBL_MAX;
+        S.st.prev_mse = A.prev2 ? A.prev2[pair] : DBL_MAX;
         S.st.mse = 0.0;
         S.st.iterations = 0;
         S.st.state = RSPCL_CONV_NOT_CONVERGED;

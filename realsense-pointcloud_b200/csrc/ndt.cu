@@ -16,8 +16,10 @@
 // Roofline: K7 reads 16 B per source point and is bounded by the FP64 pipe (hundreds of fp64 FMAs per
 // (point, voxel) pair), not by HBM; both are reported by bench.py.
 #include "grid.cuh"
+#include <cooperative_groups.h>
 #include <float.h>
 #include <math.h>
+namespace cg = cooperative_groups;
 
 int radix_sort_pairs(rspcl_ctx* ctx, unsigned long long* keys, int* vals, unsigned long long* tmp_keys, int* tmp_vals,
                      long long n);
@@ -292,30 +294,18 @@ __device__ __forceinline__ double xCh(const double* xr, const double* C, const d
          xr[2] * (C[6] * h[0] + C[7] * h[1] + C[8] * h[2]);
 }
 
-__global__ void __launch_bounds__(NT) k_ndt_eval(const float4* __restrict__ src, const int* __restrict__ count, int stride,
-                                                 const NdtEval* __restrict__ evals, NdtGridDev G, double d1, double d2,
-                                                 double* __restrict__ partials) {
-  __shared__ NdtEval E;
-  __shared__ double s_red[NT / 32][NACC];
-  const int seg = blockIdx.y;
-  if (!evals[seg].active) return;
-  for (int k = threadIdx.x; k < (int)(sizeof(NdtEval) / 4); k += NT) ((int*)&E)[k] = ((const int*)&evals[seg])[k];
-  __syncthreads();
-  const int n = count[seg];
-  const int tseg = G.shared_target ? 0 : seg;
-  const bool wantH = E.want_hessian != 0;
-  double acc[NACC];
-#pragma unroll
-  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-
-  for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
-    const float4 p = src[(size_t)seg * stride + i];
-    if (!finite3(p.x, p.y, p.z)) continue;
+// One source point against its 3x3x3 voxel neighbourhood: computeDerivatives' loop body (transform, radiusSearch over the
+// voxel centroids, updateDerivatives / updateHessian).  Shared by the per-evaluation kernel and the persistent kernel.
+// n_pairs counts the (point, voxel) pairs that contributed (roofline accounting).
+__device__ __forceinline__ void ndt_point_eval(const float4 p, const NdtEval& E, const NdtGridDev& G, int tseg, bool wantH,
+                                               double d1, double d2, double* acc, int& n_pairs) {
+  do {
+    if (!finite3(p.x, p.y, p.z)) break;
     const float3 xt = xform_point(E.T, p.x, p.y, p.z);
-    if (!finite3(xt.x, xt.y, xt.z)) continue;
+    if (!finite3(xt.x, xt.y, xt.z)) break;
     const int cx = floor_to_int_x86(fmul(xt.x, G.inv_leaf)), cy = floor_to_int_x86(fmul(xt.y, G.inv_leaf)),
               cz = floor_to_int_x86(fmul(xt.z, G.inv_leaf));
-    if (!grid_in_range(cx, cy, cz)) continue;
+    if (!grid_in_range(cx, cy, cz)) break;
     const double x[3] = {(double)p.x, (double)p.y, (double)p.z};
     // computePointDerivatives: J = [I | angular columns]
     const double J3[3] = {0.0, dot3(x, E.ja[0]), dot3(x, E.ja[1])};
@@ -351,6 +341,7 @@ __global__ void __launch_bounds__(NT) k_ndt_eval(const float4* __restrict__ src,
           e = d2 * e;
           if (e > 1 || e < 0 || e != e) continue;  // updateDerivatives returns 0: no score either
           e *= d1;
+          ++n_pairs;
           // c_inv * J.col(i) and x_trans . (c_inv * J.col(i))
           double cJ[6][3];
 #pragma unroll
@@ -397,7 +388,28 @@ __global__ void __launch_bounds__(NT) k_ndt_eval(const float4* __restrict__ src,
               }
           }
         }
-  }
+    } while (false);
+}
+
+__global__ void __launch_bounds__(NT) k_ndt_eval(const float4* __restrict__ src, const int* __restrict__ count, int stride,
+                                                 const NdtEval* __restrict__ evals, NdtGridDev G, double d1, double d2,
+                                                 double* __restrict__ partials) {
+  __shared__ NdtEval E;
+  __shared__ double s_red[NT / 32][NACC];
+  const int seg = blockIdx.y;
+  if (!evals[seg].active) return;
+  for (int k = threadIdx.x; k < (int)(sizeof(NdtEval) / 4); k += NT) ((int*)&E)[k] = ((const int*)&evals[seg])[k];
+  __syncthreads();
+  const int n = count[seg];
+  const int tseg = G.shared_target ? 0 : seg;
+  const bool wantH = E.want_hessian != 0;
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+
+  int n_pairs_unused = 0;
+  for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT)
+    ndt_point_eval(src[(size_t)seg * stride + i], E, G, tseg, wantH, d1, d2, acc, n_pairs_unused);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NACC; ++k) {
@@ -909,6 +921,131 @@ __global__ void __launch_bounds__(32) k_ndt_control(NdtState* __restrict__ st, N
 }
 
 
+// ------------------------------------------------------------------------------------------------ persistent align
+// One thread-block cluster per (source, target) pair runs the WHOLE align -- every derivative evaluation of the Newton
+// iterations and of the More-Thuente line search, the 28-sum reduction, the Newton solve and the line-search state
+// machine -- inside a single launch: no launch per evaluation, no host polling (the per-evaluation path costs ~35 us of
+// launch + control per evaluation for ~10 us of arithmetic on a 6 k-point pair).  Every CTA owns an interleaved share of
+// the source points; the partial sums are pushed into every sibling's shared memory (st.async + mbarrier, as in
+// icp_persist.cuh) and every CTA redundantly runs the identical controller, so no broadcast is needed.
+constexpr int NPT = 256;            // threads per CTA
+constexpr int NP_CLMAX = 8;
+
+struct NdtPersistSmem {
+  NdtEval E;
+  NdtState S;
+  double red[NPT / 32][NACC];
+  double xch[2][NP_CLMAX][NACC];
+  double sums[NACC];
+  unsigned long long mbar[2];
+  int finished;
+};
+
+__global__ void __launch_bounds__(NPT, 1)
+k_ndt_persist(const float4* __restrict__ src, const int* __restrict__ count, int stride, NdtState* __restrict__ st,
+              NdtEval* __restrict__ ev, NdtGridDev G, double d1, double d2, NdtCtl ctl, int max_evals,
+              unsigned long long* __restrict__ work_count /* [0] (point, voxel) pairs of gradient evaluations, [1] of Hessian ones */) {
+  __shared__ NdtPersistSmem M;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int CL = (int)cg::this_cluster().num_blocks();
+  const int crank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const int seg = blockIdx.x / CL;
+  static_assert(sizeof(NdtState) % 4 == 0 && sizeof(NdtEval) % 4 == 0, "copied as 32-bit words");
+  for (int k = tid; k < (int)(sizeof(NdtEval) / 4); k += NPT) ((unsigned*)&M.E)[k] = ((const unsigned*)&ev[seg])[k];
+  for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += NPT) ((unsigned*)&M.S)[k] = ((const unsigned*)&st[seg])[k];
+  if (tid == 0) {
+    mbar_init(smem_u32(&M.mbar[0]), 1);
+    mbar_init(smem_u32(&M.mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    M.finished = 0;
+  }
+  __syncthreads();
+  if (CL > 1) cg::this_cluster().sync();  // every CTA is running and has its barriers before anyone stores into it
+  const int n = count[seg];
+  const int tseg = G.shared_target ? 0 : seg;
+  const float4* P = src + (size_t)seg * stride;
+  int parity = 0;
+  unsigned mphase = 0;
+  unsigned long long pairs_g = 0, pairs_h = 0;
+  for (int evals = 0; evals < max_evals; ++evals) {
+    const bool wantH = M.E.want_hessian != 0;
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    int np = 0;
+    for (int i = tid * CL + crank; i < n; i += NPT * CL) ndt_point_eval(P[i], M.E, G, tseg, wantH, d1, d2, acc, np);
+    if (wantH) pairs_h += np; else pairs_g += np;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+      const double v = warp_sum(acc[k]);
+      if (lane == 0) M.red[wid][k] = v;
+    }
+    __syncthreads();
+    const int buf = parity;
+    parity ^= 1;
+    if (wid == 0) {
+      double v = 0;
+      if (lane < NACC) {
+#pragma unroll
+        for (int w = 0; w < NPT / 32; ++w) v += M.red[w][lane];
+      }
+      if (CL > 1) {
+        const unsigned mb = smem_u32(&M.mbar[buf]);
+        if (lane < NACC) {
+          const unsigned slot_addr = smem_u32(&M.xch[buf][crank][lane]);
+          for (int rk = 0; rk < CL; ++rk) st_async_f64(mapa_u32(slot_addr, rk), v, mapa_u32(mb, rk));
+        }
+        if (lane == 0) mbar_arrive_expect_tx(mb, (unsigned)(CL * NACC * sizeof(double)));
+        mbar_wait_cluster(mb, (mphase >> buf) & 1u);
+        if (lane < NACC) {
+          v = 0;
+          for (int rk = 0; rk < CL; ++rk) v += M.xch[buf][rk][lane];  // fixed rank order: identical on every CTA
+        }
+      }
+      if (lane < NACC) M.sums[lane] = v;
+      __syncwarp();
+      if (lane == 0) M.finished = ndt_control_step(&M.S, &M.E, M.sums, ctl) ? 1 : 0;
+    }
+    mphase ^= 1u << buf;
+    __syncthreads();
+    if (M.finished) break;
+  }
+  if (CL > 1) cg::this_cluster().sync();  // nobody leaves while a sibling may still store into its shared memory
+  if (crank == 0) {
+    for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += NPT) ((unsigned*)&st[seg])[k] = ((const unsigned*)&M.S)[k];
+    for (int k = tid; k < (int)(sizeof(NdtEval) / 4); k += NPT) ((unsigned*)&ev[seg])[k] = ((const unsigned*)&M.E)[k];
+  }
+  if (work_count) {
+    for (int o = 16; o > 0; o >>= 1) {
+      pairs_g += __shfl_down_sync(0xffffffffu, pairs_g, o);
+      pairs_h += __shfl_down_sync(0xffffffffu, pairs_h, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&work_count[0], pairs_g);
+      atomicAdd(&work_count[1], pairs_h);
+    }
+  }
+}
+
+// point-sharded mode, peer-memory path (see k_icp_solve_peer): CTA partials -> one-shot exchange of the 28 totals -> controller
+__global__ void __launch_bounds__(32) k_ndt_control_peer(NdtState* __restrict__ st, NdtEval* __restrict__ ev,
+                                                         const double* __restrict__ partials, int nblk, NdtCtl ctl,
+                                                         int* __restrict__ n_active, PeerX X) {
+  const int seg = blockIdx.x;
+  if (st[seg].done) return;
+  const int lane = threadIdx.x;
+  __shared__ double sums[NACC];
+  double v = 0;
+  if (lane < NACC)
+    for (int b = 0; b < nblk; ++b) v += partials[((size_t)seg * nblk + b) * NACC + lane];
+  v = peer_allreduce_warp(X, v, lane, NACC, seg);
+  if (lane < NACC) sums[lane] = v;
+  __syncwarp();
+  bool finished = false;
+  if (lane == 0) finished = ndt_control_step(&st[seg], &ev[seg], sums, ctl);
+  if (finished) atomicSub(n_active, 1);
+}
+
 __global__ void k_ndt_gather_T(const NdtState* __restrict__ st, float* __restrict__ T, int n_seg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_seg * 16) T[i] = st[i / 16].final_T[i % 16];
@@ -1030,6 +1167,11 @@ void ndt_grid_free(rspcl_ctx* ctx, NdtGridDev* G) {
 
 }  // namespace
 
+__global__ void k_counts_f64(const int* __restrict__ count, double* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)count[i];
+}
+
 extern "C" void rspcl_ndt_reference_params(rspcl_ndt_params* p) {
   p->max_iterations = 50;            // ndt:43
   p->min_points_per_voxel = 6;
@@ -1089,6 +1231,44 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   long long done_evals = 0;
   int chunk = 4, active = S;
   dim3 ge(nblk, S);
+  const char* penv = getenv("RSPCL_NDT_PERSIST");
+  if (!sharded && !(penv && penv[0] == '0')) {
+    // whole align in one launch: one cluster per pair, as many CTAs per pair as one wave of the chip allows
+    int cl = ctx->sm_count / (S > 0 ? S : 1);
+    cl = cl < 1 ? 1 : (cl > NP_CLMAX ? NP_CLMAX : cl);
+    while (cl > 1 && src->max_count_hint / cl < NPT / 2) --cl;  // tiny clouds: more CTAs only add exchange latency
+    unsigned long long* d_work = nullptr;
+    CU(ctx, scratch_alloc(ctx, &d_work, 2));
+    CU(ctx, cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cl * S));
+    cfg.blockDim = dim3(NPT);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl;
+    at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    unsigned long long hw[2] = {0, 0};
+    {
+      ProfScope prof(ctx, "k_ndt_persist", 0.0);
+      CU(ctx, cudaLaunchKernelEx(&cfg, k_ndt_persist, (const float4*)src->pts, (const int*)src->count, src->stride, st, ev, G, d1, d2, ctl,
+                                 (int)max_evals, d_work));
+      LAUNCH_CHECK(ctx);
+      prof.end();
+      if (ctx->prof_on) {
+        CU(ctx, small_d2h(ctx, hw, d_work, sizeof(hw)));
+        CU(ctx, ctx_sync(ctx));
+        // FP64 operations: per (point, voxel) pair ~135 for a gradient evaluation, ~456 with the Hessian (counted from
+        // ndt_point_eval); reported as "equivalent gradient pairs" so that one number carries both
+        prof.set_units((double)hw[0] + (double)hw[1] * (456.0 / 135.0));
+      }
+    }
+    scratch_free(ctx, d_work);
+    active = 0;
+  }
   while (active > 0 && done_evals < max_evals) {
     for (int k = 0; k < chunk; ++k) {
       {
@@ -1097,7 +1277,9 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         LAUNCH_CHECK(ctx);
       }
       ProfScope prof_c(ctx, "k_ndt_control", (double)S);
-      if (sharded) {
+      if (sharded && comm_peer_ready(ctx, S, NACC)) {
+        k_ndt_control_peer<<<S, 32, 0, ctx->stream>>>(st, ev, partials, nblk, ctl, n_active, comm_peer_next(ctx));
+      } else if (sharded) {
         k_ndt_sum_partials_active<<<S, 32, 0, ctx->stream>>>(partials, nblk, ev, totals);
         LAUNCH_CHECK(ctx);
         int rcc = comm_allreduce_f64(ctx, totals, (size_t)S * NACC);
@@ -1123,9 +1305,25 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     rc = transform_device(ctx, src, d_T, 0, aligned);
   }
   CU(ctx, ctx_sync(ctx));
+  // source sizes for trans_probability = score / input_->size() (ndt.hpp); in point-sharded mode that is the size of the
+  // WHOLE source, i.e. the shard counts summed over the ranks -- every rank then reports the same value
   std::vector<int> scnt(S);
-  CU(ctx, small_d2h(ctx, scnt.data(), src->count, S * sizeof(int)));
-  CU(ctx, ctx_sync(ctx));
+  if (sharded) {
+    std::vector<double> cd(S);
+    double* d_cnt = nullptr;
+    CU(ctx, scratch_alloc(ctx, &d_cnt, (size_t)S));
+    k_counts_f64<<<div_up(S, 128), 128, 0, ctx->stream>>>(src->count, d_cnt, S);
+    LAUNCH_CHECK(ctx);
+    int rcc = comm_allreduce_f64(ctx, d_cnt, (size_t)S);
+    if (rcc) return rcc;
+    CU(ctx, small_d2h(ctx, cd.data(), d_cnt, (size_t)S * sizeof(double)));
+    CU(ctx, ctx_sync(ctx));
+    scratch_free(ctx, d_cnt);
+    for (int s = 0; s < S; ++s) scnt[s] = (int)(cd[s] + 0.5);
+  } else {
+    CU(ctx, small_d2h(ctx, scnt.data(), src->count, S * sizeof(int)));
+    CU(ctx, ctx_sync(ctx));
+  }
   for (int s = 0; s < S; ++s) {
     memcpy(h_results[s].T, hst[s].final_T, 64);
     h_results[s].converged = hst[s].converged;

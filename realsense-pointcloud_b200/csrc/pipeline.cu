@@ -60,7 +60,176 @@ __global__ void k_transform2_gather(const float4* __restrict__ frames, int w_h, 
   }
 }
 
+// one cloud segment moved by two transforms in a row (exactly two pcl::transformPointCloud calls) into out[0 .. n)
+__global__ void k_transform2_seg(const float4* __restrict__ in, const int* __restrict__ in_count, int n_fixed,
+                                 const float* __restrict__ Ta, const float* __restrict__ Tb, float4* __restrict__ out) {
+  __shared__ float A[16], B[16];
+  if (threadIdx.x < 16) {
+    A[threadIdx.x] = Ta[threadIdx.x];
+    B[threadIdx.x] = Tb[threadIdx.x];
+  }
+  __syncthreads();
+  const int n = in_count ? *in_count : n_fixed;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = in[i];
+    if (finite3(p.x, p.y, p.z)) {
+      float3 q = xform_point(A, p.x, p.y, p.z);
+      q = xform_point(B, q.x, q.y, q.z);
+      p.x = q.x;
+      p.y = q.y;
+      p.z = q.z;
+    }
+    out[i] = p;
+  }
+}
+
+__global__ void k_copy_points(const float4* __restrict__ in, int n, float4* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i];
+}
+
 }  // namespace
+
+extern "C" int rspcl_register_sequence(rspcl_ctx* ctx, const rspcl_cloud* frames, int coarse_kind, const rspcl_icp_params* icp,
+                                       const rspcl_ndt_params* ndt, const float leaf[3], float t_low, float t_high,
+                                       const float* guess, rspcl_pair_result* results, rspcl_cloud* out_global,
+                                       rspcl_cloud* out_target) {
+  if (!ctx || !frames || !icp || !leaf || !guess || !results || !out_global) return RSPCL_ERR_ARG;
+  if (coarse_kind == RSPCL_COARSE_NDT && !ndt) return RSPCL_ERR_ARG;
+  if (frames->height <= 0) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "register_sequence: frames are not organized");
+  const int F = frames->n_seg, npx = frames->width * frames->height;
+  if (out_global->n_seg != 1 || (long long)out_global->stride < (long long)F * npx)
+    RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "register_sequence: out_global needs 1 segment of stride >= %lld", (long long)F * npx);
+  CU(ctx, cudaSetDevice(ctx->device));
+
+  // phase 1 (types.hpp:34-38) + the voxel filter of every edge cloud (icp:59-60,75-76)
+  TmpCloud E(ctx);
+  int rc = E.init(F, npx);
+  if (rc) RSPCL_FAIL(ctx, rc, "register_sequence: scratch allocation failed");
+  rc = rspcl_edge_extract(ctx, frames, t_low, t_high, &E.c, nullptr);
+  if (rc) return rc;
+  rc = voxel_approx_device(ctx, &E.c, leaf, &E.c);
+  if (rc) return rc;
+  std::vector<int> vcnt;
+  rc = refresh_count_hint(ctx, &E.c, &vcnt);
+  if (rc) return rc;
+  long long cap = 0;
+  for (int v : vcnt) cap += v;
+  if (cap < 1) cap = 1;
+  if (out_target && (out_target->n_seg != 1 || (long long)out_target->stride < cap))
+    RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "register_sequence: out_target needs 1 segment of stride >= %lld", cap);
+
+  Scratch scr(ctx);
+  float4* tbuf = nullptr;   // the accumulating edge target occupies tbuf[cap - n_t .. cap)
+  int* d_cnt = nullptr;     // [0] target count, [1] coarse-aligned source count (NDT path)
+  float* d_T = nullptr;     // guess | T_coarse | T_fine of the current frame
+  CU(ctx, scr.alloc(&tbuf, (size_t)cap));
+  CU(ctx, scr.alloc(&d_cnt, 2));
+  CU(ctx, scr.alloc(&d_T, 48));
+  auto nblk = [&](long long n) {
+    long long b = (n + 255) / 256, m = 8LL * ctx->sm_count;
+    return (unsigned)(b < 1 ? 1 : (b > m ? m : b));
+  };
+  long long n_t = vcnt[0], n_g = npx;
+  k_copy_points<<<nblk(n_t), 256, 0, ctx->stream>>>(E.c.pts, (int)n_t, tbuf + (cap - n_t));                 // target = clouds[0].first
+  LAUNCH_CHECK(ctx);
+  k_copy_points<<<nblk(npx), 256, 0, ctx->stream>>>(frames->pts, npx, out_global->pts);                      // icp:57
+  LAUNCH_CHECK(ctx);
+  memset(&results[0], 0, sizeof(rspcl_pair_result));
+  for (int i = 0; i < 16; ++i) results[0].T_coarse[i] = results[0].T_fine[i] = (i % 5 == 0) ? 1.f : 0.f;
+  results[0].converged = 1;
+  results[0].n_src = results[0].n_tgt = vcnt[0];
+
+  TmpCloud Ac(ctx);
+  if (coarse_kind == RSPCL_COARSE_NDT && Ac.init(1, E.c.max_count_hint > 0 ? E.c.max_count_hint : 1))
+    RSPCL_FAIL(ctx, RSPCL_ERR_CUDA, "register_sequence: scratch allocation failed");
+  double prev_coarse = DBL_MAX, prev_fine = DBL_MAX;  // one PCL object per stage lives across the frames (icp:35,41)
+  for (int k = 1; k < F; ++k) {
+    const int m = vcnt[k];
+    rspcl_cloud src, tgt;  // single-segment views
+    src.pts = E.c.pts + (size_t)k * E.c.stride;
+    src.count = E.c.count + k;
+    src.n_seg = 1;
+    src.stride = E.c.stride;
+    src.max_count_hint = m;
+    const int nt_i = (int)n_t;
+    CU(ctx, small_h2d(ctx, d_cnt, &nt_i, sizeof(int)));
+    tgt.pts = tbuf + (cap - n_t);
+    tgt.count = d_cnt;
+    tgt.n_seg = 1;
+    tgt.stride = (int)n_t;
+    tgt.max_count_hint = (int)n_t;
+    CU(ctx, small_h2d(ctx, d_T, guess + (size_t)k * 16, 16 * sizeof(float)));
+    rspcl_pair_result& R = results[k];
+    memset(&R, 0, sizeof(R));
+    rspcl_icp_result fine;
+    fine.prev_mse = prev_fine;
+    const float4* fine_in = src.pts;  // what the two transforms below are applied to
+    const int* fine_in_count = src.count;
+    if (coarse_kind == RSPCL_COARSE_NDT) {
+      rspcl_ndt_result nr;
+      rc = ndt_align_device(ctx, &src, &tgt, ndt, d_T, &nr, &Ac.c);
+      if (rc) return rc;
+      memcpy(R.T_coarse, nr.T, 64);
+      R.coarse_iterations = nr.iterations;
+      IcpAlignOpts o;
+      o.h_src_counts = &m;
+      rc = icp_align_device(ctx, &Ac.c, &tgt, icp, nullptr, &fine, nullptr, o);
+      if (rc) return rc;
+    } else {
+      rspcl_icp_result cr;
+      cr.prev_mse = prev_coarse;
+      IcpAlignOpts o;
+      o.h_results2 = &fine;
+      o.h_src_counts = &m;
+      rc = icp_align_device(ctx, &src, &tgt, icp, d_T, &cr, nullptr, o);
+      if (rc) return rc;
+      memcpy(R.T_coarse, cr.T, 64);
+      R.coarse_iterations = cr.iterations;
+      prev_coarse = cr.prev_mse;
+    }
+    prev_fine = fine.prev_mse;
+    memcpy(R.T_fine, fine.T, 64);
+    R.converged = fine.converged;
+    R.fine_iterations = fine.iterations;
+    R.n_corr = fine.n_corr;
+    R.mse = fine.mse;
+    R.n_src = m;
+    R.n_tgt = (int)n_t;
+    if (!fine.converged) continue;  // failed frames are skipped silently (icp:113-123)
+    CU(ctx, small_h2d(ctx, d_T + 16, R.T_coarse, 16 * sizeof(float)));
+    CU(ctx, small_h2d(ctx, d_T + 32, R.T_fine, 16 * sizeof(float)));
+    // *target = *icp_aligned + *target (icp:119): the fine-aligned edges go in FRONT of the target
+    if (m > 0) {
+      k_transform2_seg<<<nblk(m), 256, 0, ctx->stream>>>(fine_in, fine_in_count, m, d_T + 16, d_T + 32, tbuf + (cap - n_t - m));
+      LAUNCH_CHECK(ctx);
+      n_t += m;
+    }
+    // *global += transformed (icp:116-117,120)
+    {
+      ProfScope prof(ctx, "k_transform2", (double)npx);
+      k_transform2_seg<<<nblk(npx), 256, 0, ctx->stream>>>(frames->pts + (size_t)k * frames->stride, nullptr, npx, d_T + 16, d_T + 32,
+                                                          out_global->pts + n_g);
+      LAUNCH_CHECK(ctx);
+    }
+    n_g += npx;
+  }
+  const int ng_i = (int)n_g, nt_i = (int)n_t;
+  CU(ctx, small_h2d(ctx, out_global->count, &ng_i, sizeof(int)));
+  out_global->max_count_hint = ng_i;
+  out_global->width = out_global->height = 0;
+  invalidate_gray(out_global);
+  if (out_target) {
+    k_copy_points<<<nblk(n_t), 256, 0, ctx->stream>>>(tbuf + (cap - n_t), nt_i, out_target->pts);
+    LAUNCH_CHECK(ctx);
+    CU(ctx, small_h2d(ctx, out_target->count, &nt_i, sizeof(int)));
+    out_target->max_count_hint = nt_i;
+    out_target->width = out_target->height = 0;
+    invalidate_gray(out_target);
+  }
+  CU(ctx, ctx_sync(ctx));
+  scr.ok();
+  return RSPCL_OK;
+}
 
 extern "C" int rspcl_register_pairs(rspcl_ctx* ctx, const rspcl_cloud* frames, const int32_t* src_idx, const int32_t* tgt_idx,
                                     int n_pairs, int coarse_kind, const rspcl_icp_params* icp, const rspcl_ndt_params* ndt,

@@ -6,6 +6,10 @@
 //       --imu FILE: IMU trace ("ts_ms kind x y z" rows, kind 0 = gyro, 1 = accel) followed by a line "frames t0 t1 ..";
 //       the angle triples of the complementary filter (rotation_estimator.hpp) replace the fixed-degree guess, as in
 //       the reference's capture modes (main.cpp:129).
+//       --per-call: run the sweep through the PCL-shaped objects call by call (upload / download per call) instead of the
+//       device-resident rspcl_register_sequence (default).
+//       --dump-pairs: also write DIR/<prefix>-{src,tgt,coarse}-<k>.pcd, the exact inputs of frame k's coarse and fine
+//       stages (parity aid, in the spirit of the reference's own dataset/edge-<i>.pcd dumps, icp:66-69).
 //   rs_pcl_b200 [--dataset DIR] --edges <file>
 //       extract_edge_features of DIR/<file> (main.cpp:58-62); prints the edge count, writes DIR/<file>.edges.pcd.
 // The GL viewer loops of the reference (main.cpp:65-73,90-98) and the capture modes are out of scope.
@@ -13,27 +17,39 @@
 #include <cstring>
 #include "rspcl.hpp"
 
-static void print_json(const std::vector<rspcl::Matrix4f>& T, const std::vector<int>& acc, size_t npts) {
-  std::printf("{\"points\": %zu, \"accepted\": [", npts);
-  for (size_t i = 0; i < acc.size(); ++i) std::printf("%s%d", i ? ", " : "", acc[i]);
-  std::printf("], \"transforms\": [");
+static void print_mats(const char* key, const std::vector<rspcl::Matrix4f>& T) {
+  std::printf(", \"%s\": [", key);
   for (size_t k = 0; k < T.size(); ++k) {
     std::printf("%s[", k ? ", " : "");
     for (int r = 0; r < 4; ++r)
       for (int c = 0; c < 4; ++c) std::printf("%s%.9g", (r || c) ? ", " : "", T[k](r, c));  // row-major rows
     std::printf("]");
   }
-  std::printf("]}\n");
+  std::printf("]");
+}
+
+static void print_json(const std::vector<rspcl::Matrix4f>& T, const std::vector<int>& acc, size_t npts,
+                       const std::vector<rspcl::Matrix4f>& Tc, const std::vector<rspcl::Matrix4f>& Tf) {
+  std::printf("{\"points\": %zu, \"accepted\": [", npts);
+  for (size_t i = 0; i < acc.size(); ++i) std::printf("%s%d", i ? ", " : "", acc[i]);
+  std::printf("]");
+  print_mats("transforms", T);
+  if (!Tc.empty()) print_mats("coarse", Tc);
+  if (!Tf.empty()) print_mats("fine", Tf);
+  std::printf("}\n");
 }
 
 int main(int argc, char** argv) {
   try {
     std::string dir = "dataset", scheme = "ndt", imu_path;
+    bool dump_pairs = false, per_call = false;
     std::vector<std::string> a;
     for (int i = 1; i < argc; ++i) {
       if (!std::strcmp(argv[i], "--dataset") && i + 1 < argc) dir = argv[++i];
       else if (!std::strcmp(argv[i], "--scheme") && i + 1 < argc) scheme = argv[++i];
       else if (!std::strcmp(argv[i], "--imu") && i + 1 < argc) imu_path = argv[++i];
+      else if (!std::strcmp(argv[i], "--dump-pairs")) dump_pairs = true;
+      else if (!std::strcmp(argv[i], "--per-call")) per_call = true;
       else a.push_back(argv[i]);
     }
     if (a.size() >= 2 && a[0] == "--edges") {
@@ -62,7 +78,7 @@ int main(int argc, char** argv) {
         clouds.push_back(c);
       }
       rgb_point_cloud_pointer result;
-      std::vector<rspcl::Matrix4f> T;
+      std::vector<rspcl::Matrix4f> T, Tc, Tf;
       std::vector<int> acc;
       std::vector<rs_float3> thetas;
       if (!imu_path.empty()) {
@@ -93,16 +109,20 @@ int main(int argc, char** argv) {
       } else if (scheme == "icp") {
         ICPEdgeBasedRegistration s_imu(thetas), s_fix(rads);
         ICPEdgeBasedRegistration& s = thetas.empty() ? s_fix : s_imu;
+        if (dump_pairs) s.dump_pairs_prefix = dir + "/" + prefix;
+        s.device_resident = !per_call;
         result = s.registration(clouds);
-        T = s.transforms, acc = s.accepted;
+        T = s.transforms, acc = s.accepted, Tc = s.coarse_transforms, Tf = s.fine_transforms;
       } else {
         NDTEdgeBasedRegistration s_imu(thetas), s_fix(rads);
         NDTEdgeBasedRegistration& s = thetas.empty() ? s_fix : s_imu;
+        if (dump_pairs) s.dump_pairs_prefix = dir + "/" + prefix;
+        s.device_resident = !per_call;
         result = s.registration(clouds);
-        T = s.transforms, acc = s.accepted;
+        T = s.transforms, acc = s.accepted, Tc = s.coarse_transforms, Tf = s.fine_transforms;
       }
       rspcl::io::savePCDFileBinary(dir + "/" + prefix + "-registration", *result);
-      print_json(T, acc, result->size());
+      print_json(T, acc, result->size(), Tc, Tf);
       return 0;
     }
     std::fprintf(stderr, "usage: rs_pcl_b200 [--dataset DIR] [--scheme ndt|icp|incremental] [--imu FILE] --registration <prefix> [deg] <N>\n"

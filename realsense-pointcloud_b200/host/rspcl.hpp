@@ -228,6 +228,21 @@ class DeviceCloud {
                                            org ? static_cast<int>(c.width) : 0, org ? static_cast<int>(c.height) : 0),
                         "cloud_upload");
   }
+  // n organized clouds of equal dimensions -> the n segments of this batch
+  template <typename PtrVec>
+  void upload_batch(const PtrVec& clouds) {
+    std::vector<PointXYZRGB> all;
+    std::vector<std::int32_t> counts;
+    for (const auto& c : clouds) {
+      all.insert(all.end(), c->points.begin(), c->points.end());
+      counts.push_back(static_cast<std::int32_t>(c->size()));
+    }
+    Device::get().check(rspcl_cloud_upload(Device::get().ctx(), h_, all.data(), RSPCL_LAYOUT_PCL32, counts.data(),
+                                           static_cast<int>(counts.size()), static_cast<int>(clouds[0]->width),
+                                           static_cast<int>(clouds[0]->height)),
+                        "cloud_upload");
+    Device::get().check(rspcl_ctx_sync(Device::get().ctx()), "sync");  // `all` is pageable staging
+  }
   void download(PointCloud& out) const {
     std::int32_t n = 0;
     Device::get().check(rspcl_cloud_counts(Device::get().ctx(), h_, &n), "cloud_counts");
@@ -404,6 +419,12 @@ class BlurFilter {
   }
 };
 
+namespace rspcl {
+namespace io {
+inline void savePCDFileBinary(const std::string& path, const PointCloud& cloud);  // defined below
+}
+}  // namespace rspcl
+
 // ------------------------------------------------------------------ types.hpp:14-44
 class RegistrationScheme {
  public:
@@ -430,6 +451,59 @@ class EdgeBasedRegistrationBase : public TwoPhaseRegistrationScheme {
  public:
   rgb_point_cloud_pointer extract_features(rgb_point_cloud_pointer cloud) override { return rspcl::extract_edge_features(cloud); }
 
+  // types.hpp:30-43.  By default the whole sweep runs device-resident through rspcl_register_sequence (one upload of the
+  // frames, one download of the merged cloud, the edge target accumulating in HBM); device_resident = false takes the
+  // PCL-shaped path below call by call (each PCL-style object uploads its inputs and downloads its output), which is
+  // what a maintainer gets when only the PCL classes inside the reference's own loop are swapped (INTEGRATION.md level 1).
+  rgb_point_cloud_pointer registration(std::vector<rgb_point_cloud_pointer>& clouds) override {
+    if (!device_resident || !dump_pairs_prefix.empty() || clouds.empty() || !clouds[0]->isOrganized())
+      return TwoPhaseRegistrationScheme::registration(clouds);
+    for (auto& c : clouds)
+      if (c->width != clouds[0]->width || c->height != clouds[0]->height) return TwoPhaseRegistrationScheme::registration(clouds);
+    if (use_imu) assert(clouds.size() == thetas.size());
+    const std::size_t n = clouds.size();
+    const int w = static_cast<int>(clouds[0]->width), h = static_cast<int>(clouds[0]->height);
+    std::vector<float> guess(n * 16, 0.f);
+    float acc_rads = 0.f;
+    for (std::size_t k = 1; k < n; ++k) {
+      rspcl::Matrix4f g;
+      if (use_imu) {
+        const rs_float3 zero = thetas[0] * -1.0f;
+        thetas[k].add(zero.x, zero.y, zero.z);
+        g = imu_guess(thetas[k]);
+      } else {
+        acc_rads += rads;
+        g = rspcl::Matrix4f::AngleAxis(acc_rads, 1);
+      }
+      std::memcpy(&guess[k * 16], g.data(), 64);
+    }
+    rspcl::Device& dev = rspcl::Device::get();
+    rspcl::DeviceCloud frames(static_cast<int>(n), w * h), merged(1, static_cast<int>(n) * w * h);
+    frames.upload_batch(clouds);
+    std::vector<rspcl_pair_result> res(n);
+    rspcl_icp_params ip;
+    rspcl_icp_reference_params(&ip);  // icp:42-45,49-52 / ndt:47-50
+    rspcl_ndt_params np;
+    rspcl_ndt_reference_params(&np);  // ndt:39-43
+    const float leaf[3] = {0.01f, 0.01f, 0.01f};
+    dev.check(rspcl_register_sequence(dev.ctx(), frames.handle(), coarse_kind(), &ip, &np, leaf, 40.f, 100.f, guess.data(), res.data(),
+                                      merged.handle(), nullptr),
+              "register_sequence");
+    transforms.assign(n, rspcl::Matrix4f::Identity());
+    coarse_transforms = fine_transforms = transforms;
+    accepted.assign(n, 0);
+    for (std::size_t k = 0; k < n; ++k) {
+      std::memcpy(coarse_transforms[k].data(), res[k].T_coarse, 64);
+      std::memcpy(fine_transforms[k].data(), res[k].T_fine, 64);
+      transforms[k] = fine_transforms[k] * coarse_transforms[k];
+      accepted[k] = res[k].converged;
+    }
+    rgb_point_cloud_pointer global(new rgb_point_cloud);
+    merged.download(*global);
+    return global;
+  }
+  bool device_resident = true;
+
   rgb_point_cloud_pointer global_registration(FeaturePairs& clouds) override {
     if (use_imu) assert(clouds.size() == thetas.size());
     rspcl::ApproximateVoxelGrid voxel;
@@ -445,6 +519,7 @@ class EdgeBasedRegistrationBase : public TwoPhaseRegistrationScheme {
     voxel.filter(*target);
 
     transforms.assign(clouds.size(), rspcl::Matrix4f::Identity());
+    coarse_transforms = fine_transforms = transforms;
     accepted.assign(clouds.size(), 0);
     accepted[0] = 1;
     float acc_rads = 0.f;
@@ -461,10 +536,18 @@ class EdgeBasedRegistrationBase : public TwoPhaseRegistrationScheme {
         acc_rads += rads;
         guess = rspcl::Matrix4f::AngleAxis(acc_rads, 1);
       }
+      if (!dump_pairs_prefix.empty()) {  // parity aid: the exact inputs of this frame's stages (like icp:68's edge dumps)
+        rspcl::io::savePCDFileBinary(dump_pairs_prefix + "-src-" + std::to_string(k) + ".pcd", *down);
+        rspcl::io::savePCDFileBinary(dump_pairs_prefix + "-tgt-" + std::to_string(k) + ".pcd", *target);
+      }
       const rspcl::Matrix4f T_coarse = run_coarse(down, target, guess, *coarse_out);
+      if (!dump_pairs_prefix.empty())
+        rspcl::io::savePCDFileBinary(dump_pairs_prefix + "-coarse-" + std::to_string(k) + ".pcd", *coarse_out);
       fine.setInputSource(coarse_out);
       fine.setInputTarget(target);
       fine.align(*fine_out);
+      coarse_transforms[k] = T_coarse;
+      fine_transforms[k] = fine.getFinalTransformation();
       transforms[k] = fine.getFinalTransformation() * T_coarse;
       if (!fine.hasConverged()) continue;  // failed frames are skipped silently (icp:113-123)
       accepted[k] = 1;
@@ -478,7 +561,9 @@ class EdgeBasedRegistrationBase : public TwoPhaseRegistrationScheme {
   }
 
   std::vector<rspcl::Matrix4f> transforms;  // per frame: T_fine * T_coarse (identity for frame 0)
+  std::vector<rspcl::Matrix4f> coarse_transforms, fine_transforms;
   std::vector<int> accepted;
+  std::string dump_pairs_prefix;  // non-empty: write <prefix>-{src,tgt,coarse}-<k>.pcd, the inputs of every frame's stages
 
  protected:
   static void configure_icp(rspcl::IterativeClosestPoint& icp) {  // icp:42-45,49-52 / ndt:47-50
@@ -487,6 +572,7 @@ class EdgeBasedRegistrationBase : public TwoPhaseRegistrationScheme {
     icp.setTransformationEpsilon(1);
     icp.setEuclideanFitnessEpsilon(1000);
   }
+  virtual int coarse_kind() const = 0;  // RSPCL_COARSE_ICP / RSPCL_COARSE_NDT
   virtual void prepare_coarse() = 0;
   virtual rspcl::Matrix4f imu_guess(const rs_float3& theta) const = 0;
   virtual rspcl::Matrix4f run_coarse(rgb_point_cloud_pointer src, rgb_point_cloud_pointer tgt, const rspcl::Matrix4f& guess,
@@ -503,6 +589,7 @@ class ICPEdgeBasedRegistration : public EdgeBasedRegistrationBase {
   explicit ICPEdgeBasedRegistration(float usr_def_rads) { rads = usr_def_rads; }
 
  protected:
+  int coarse_kind() const override { return RSPCL_COARSE_ICP; }
   void prepare_coarse() override {
     coarse_.reset(new rspcl::IterativeClosestPoint);
     configure_icp(*coarse_);
@@ -529,6 +616,7 @@ class NDTEdgeBasedRegistration : public EdgeBasedRegistrationBase {
   explicit NDTEdgeBasedRegistration(float usr_def_rads) { rads = usr_def_rads; }
 
  protected:
+  int coarse_kind() const override { return RSPCL_COARSE_NDT; }
   void prepare_coarse() override {
     ndt_.reset(new rspcl::NormalDistributionsTransform);
     ndt_->setTransformationEpsilon(0.01);  // ndt:39-43
@@ -584,19 +672,28 @@ class IncrementalICP : public RegistrationScheme {
 namespace rspcl {
 namespace io {
 inline void loadPCDFile(const std::string& path, PointCloud& cloud) {
+  // pcl::io::loadPCDFile for the field layouts the reference reads and writes (main.cpp:81,103; examples/visualizer/*.pcd):
+  // x y z [rgb|rgba], every field 4 bytes, COUNT 1.  TYPE decides how the colour is parsed: F = the float whose BITS are
+  // the packed bgra (how PCL writes PointXYZRGB), U / I = the packed integer itself (exampleTemp.pcd: "TYPE F F F U").
   std::ifstream f(path, std::ios::binary);
   if (!f) throw Error("cannot open " + path);
   std::string line, data;
   std::size_t n = 0;
   std::uint32_t w = 0, h = 1;
-  std::vector<std::string> fields;
+  std::vector<std::string> fields, types;
+  std::vector<int> sizes, counts;
   while (std::getline(f, line)) {
     std::istringstream ss(line);
-    std::string key;
+    std::string key, t;
     ss >> key;
     if (key == "FIELDS") {
-      std::string t;
       while (ss >> t) fields.push_back(t);
+    } else if (key == "SIZE") {
+      while (ss >> t) sizes.push_back(std::atoi(t.c_str()));
+    } else if (key == "TYPE") {
+      while (ss >> t) types.push_back(t);
+    } else if (key == "COUNT") {
+      while (ss >> t) counts.push_back(std::atoi(t.c_str()));
     } else if (key == "WIDTH") ss >> w;
     else if (key == "HEIGHT") ss >> h;
     else if (key == "POINTS") ss >> n;
@@ -605,30 +702,51 @@ inline void loadPCDFile(const std::string& path, PointCloud& cloud) {
       break;
     }
   }
-  if (fields.size() < 3) throw Error("unsupported PCD fields in " + path);
-  const bool has_rgb = fields.size() >= 4;
+  if (fields.size() < 3 || fields[0] != "x" || fields[1] != "y" || fields[2] != "z")
+    throw Error("unsupported PCD fields in " + path + " (need x y z [rgb|rgba] first)");
+  if (types.empty()) types.assign(fields.size(), "F");
+  if (sizes.empty()) sizes.assign(fields.size(), 4);
+  if (counts.empty()) counts.assign(fields.size(), 1);
+  if (types.size() != fields.size() || sizes.size() != fields.size() || counts.size() != fields.size())
+    throw Error("inconsistent PCD header in " + path);
+  for (std::size_t k = 0; k < fields.size(); ++k) {
+    if (counts[k] != 1) throw Error("unsupported PCD COUNT (must be 1) in " + path);
+    if (k < 4 && sizes[k] != 4) throw Error("unsupported PCD SIZE (x y z rgb must be 4 bytes) in " + path);
+    if (k < 3 && types[k] != "F") throw Error("unsupported PCD TYPE (x y z must be F) in " + path);
+  }
+  const bool has_rgb = fields.size() >= 4 && (fields[3] == "rgb" || fields[3] == "rgba");
+  const bool rgb_is_int = has_rgb && types[3] != "F";
+  std::size_t row_bytes = 0;
+  for (int sz : sizes) row_bytes += static_cast<std::size_t>(sz);
   cloud.points.assign(n, PointXYZRGB());
   cloud.width = w;
   cloud.height = h;
   if (data == "binary") {
-    std::vector<float> row(fields.size());
+    std::vector<char> row(row_bytes);
     for (std::size_t i = 0; i < n; ++i) {
-      f.read(reinterpret_cast<char*>(row.data()), static_cast<std::streamsize>(row.size() * 4));
-      cloud.points[i].x = row[0], cloud.points[i].y = row[1], cloud.points[i].z = row[2];
-      if (has_rgb) std::memcpy(&cloud.points[i].rgba, &row[3], 4);
+      f.read(row.data(), static_cast<std::streamsize>(row_bytes));
+      if (!f) throw Error("truncated PCD data in " + path);
+      std::memcpy(&cloud.points[i].x, row.data(), 4);
+      std::memcpy(&cloud.points[i].y, row.data() + 4, 4);
+      std::memcpy(&cloud.points[i].z, row.data() + 8, 4);
+      if (has_rgb) std::memcpy(&cloud.points[i].rgba, row.data() + 12, 4);  // float bits or packed integer: the same 4 bytes
     }
   } else if (data == "ascii") {
     for (std::size_t i = 0; i < n; ++i) {
-      double v[4] = {0, 0, 0, 0};
       for (std::size_t k = 0; k < fields.size(); ++k) {
-        double t;
-        f >> t;
-        if (k < 4) v[k] = t;
-      }
-      cloud.points[i].x = float(v[0]), cloud.points[i].y = float(v[1]), cloud.points[i].z = float(v[2]);
-      if (has_rgb) {
-        float rgb = float(v[3]);
-        std::memcpy(&cloud.points[i].rgba, &rgb, 4);
+        std::string tok;
+        if (!(f >> tok)) throw Error("truncated PCD data in " + path);
+        if (k < 3) {
+          const float v = std::strtof(tok.c_str(), nullptr);
+          (k == 0 ? cloud.points[i].x : k == 1 ? cloud.points[i].y : cloud.points[i].z) = v;
+        } else if (k == 3 && has_rgb) {
+          if (rgb_is_int) {
+            cloud.points[i].rgba = static_cast<std::uint32_t>(std::strtoull(tok.c_str(), nullptr, 10));
+          } else {
+            const float rgb = std::strtof(tok.c_str(), nullptr);
+            std::memcpy(&cloud.points[i].rgba, &rgb, 4);
+          }
+        }
       }
     }
   } else {

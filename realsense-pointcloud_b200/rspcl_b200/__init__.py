@@ -62,10 +62,10 @@ EXPORTS = [
     "rspcl_ctx_create", "rspcl_ctx_destroy", "rspcl_last_error", "rspcl_ctx_sync", "rspcl_timer_start",
     "rspcl_timer_stop", "rspcl_timer_mark", "rspcl_timer_span", "rspcl_launch_count", "rspcl_profile_enable", "rspcl_profile_reset", "rspcl_profile_get", "rspcl_host_alloc", "rspcl_host_free", "rspcl_cloud_create",
     "rspcl_cloud_destroy", "rspcl_cloud_n_seg", "rspcl_cloud_stride", "rspcl_cloud_dims", "rspcl_cloud_upload",
-    "rspcl_cloud_counts", "rspcl_cloud_download", "rspcl_crop35", "rspcl_edge_extract", "rspcl_voxel_approx",
+    "rspcl_cloud_counts", "rspcl_cloud_download", "rspcl_cloud_invalidate_gray", "rspcl_cloud_download_xyz_pcl32", "rspcl_crop35", "rspcl_edge_extract", "rspcl_voxel_approx",
     "rspcl_voxel_keys", "rspcl_transform", "rspcl_concat", "rspcl_cloud_copy_segment", "rspcl_icp_reference_params",
     "rspcl_icp_align", "rspcl_icp_align_dump", "rspcl_fitness", "rspcl_nearest", "rspcl_ndt_reference_params", "rspcl_ndt_align",
-    "rspcl_ndt_voxels", "rspcl_ndt_derivatives", "rspcl_register_pairs", "rspcl_comm_unique_id", "rspcl_comm_init",
+    "rspcl_ndt_voxels", "rspcl_ndt_derivatives", "rspcl_register_pairs", "rspcl_register_sequence", "rspcl_comm_unique_id", "rspcl_comm_init",
     "rspcl_comm_destroy", "rspcl_icp_align_sharded", "rspcl_ndt_align_sharded",
 ]
 
@@ -270,6 +270,9 @@ class Cloud:
             o += n
         return out
 
+    def invalidate_gray(self):
+        self.ctx.check(lib().rspcl_cloud_invalidate_gray(self.ctx.h, self.h))
+
     def dims(self):
         w, h = C.c_int(), C.c_int()
         lib().rspcl_cloud_dims(self.h, C.byref(w), C.byref(h))
@@ -432,6 +435,24 @@ def register_pairs(ctx, frames, src_idx, tgt_idx, coarse=COARSE_ICP, icp=None, n
                                          _p(lf), C.c_float(t_low), C.c_float(t_high), _p(g), res,
                                          out_transformed.h if out_transformed is not None else None))
     return res
+
+
+def register_sequence(ctx, frames, guesses, coarse=COARSE_NDT, icp=None, ndt=None, leaf=(0.01, 0.01, 0.01), t_low=40.0,
+                      t_high=100.0, out_global=None, want_target=False, target_capacity=None):
+    """The reference's accumulating-target loop for one sweep, device-resident (rspcl_register_sequence).
+    guesses: [n_frames, 4, 4] (entry 0 unused).  Returns (results, merged cloud, final edge target or None)."""
+    icp = icp or icp_params()
+    ndt = ndt or ndt_params()
+    n = frames.n_seg
+    w, h = frames.dims()
+    lf = np.asarray(leaf, np.float32)
+    g = mats_to_c(guesses, n)
+    res = (PairResult * n)()
+    out = out_global if out_global is not None else Cloud(ctx, 1, n * w * h)
+    tgt = Cloud(ctx, 1, int(target_capacity or n * w * h // 4)) if want_target else None
+    ctx.check(lib().rspcl_register_sequence(ctx.h, frames.h, int(coarse), C.byref(icp), C.byref(ndt), _p(lf), C.c_float(t_low),
+                                            C.c_float(t_high), _p(g), res, out.h, tgt.h if tgt is not None else None))
+    return res, out, tgt
 
 
 # -------------------------------------------------------------------- point-sharded multi-GPU mode

@@ -514,3 +514,47 @@ def test_icp_gate_as_large_as_the_scene(ctx):
     assert res[0]["n_corr"] == o["n_corr"] == len(src)
     ang, tr = pose_err(res[0]["T"], o["T"])
     assert ang < 1e-4 and tr < 1e-4
+
+
+# ------------------------------------------------------------------ sequential schemes, device-resident (row f3)
+@pytest.mark.parametrize("scheme", ["icp", "ndt"])
+def test_register_sequence_matches_oracle_scheme(ctx, sweep3, scheme):
+    """rspcl_register_sequence = the reference's accumulating-target loop (icp:71-124 / ndt:64-112) without leaving HBM:
+    transforms against the oracle's line-by-line scheme, merged cloud order (icp:120) and the prepend order of the target
+    (icp:119: new points first)."""
+    fr, Tgt = sweep3
+    frames = ctx.upload(list(fr), W, H)
+    rads = np.float32(-0.523599)
+    guesses = np.stack([np.eye(4)] * 3)
+    acc = np.float32(0)
+    for k in (1, 2):
+        acc = np.float32(acc + rads)
+        guesses[k][:3, :3] = gen_scene.rot_y(float(acc))
+    res, merged, target = R.register_sequence(ctx, frames, guesses, R.COARSE_NDT if scheme == "ndt" else R.COARSE_ICP,
+                                              want_target=True)
+    o = orc.scheme_edge(fr.reshape(-1), W, H, scheme)
+    assert [int(r.converged) for r in res] == o["accepted"].tolist() == [1, 1, 1]
+    strict = (1,) if scheme == "ndt" else (1, 2)   # chained NDT: see test_gpu_facade.py / DESIGN section 5
+    for k in (1, 2):
+        T = R.c_to_mat(res[k].T_fine).astype(np.float64) @ R.c_to_mat(res[k].T_coarse).astype(np.float64)
+        ang, tr = pose_err(T, o["T"][k])
+        if k in strict:
+            assert ang < 1e-4 and tr < 1e-4, (scheme, k, ang, tr)
+        else:
+            assert ang < 0.02 and tr < 0.03, (scheme, k, ang, tr)
+        assert res[k].coarse_iterations >= 1 and res[k].fine_iterations == 1
+    g = merged.download()[0]
+    assert len(g) == len(o["global"]) == 3 * W * H
+    assert np.array_equal(g[:W * H].view(np.uint32), fr[0].view(np.uint32))
+    assert np.array_equal(g["rgba"], o["global"]["rgba"])
+    n_strict = (max(strict) + 1) * W * H
+    for a in "xyz":
+        assert np.abs(g[a][:n_strict] - o["global"][a][:n_strict]).max() < 5e-4
+    # the final edge target: frame 2's fine-aligned edges first, then frame 1's, then frame 0's voxel-filtered edges
+    t = target.download()[0]
+    v = [orc.approx_voxel(orc.extract_edges(f, W, H)[0]) for f in fr]
+    assert len(t) == sum(len(x) for x in v)
+    assert np.array_equal(t[len(v[2]) + len(v[1]):].view(np.uint32), v[0].view(np.uint32))
+    for k, lo in ((2, 0), (1, len(v[2]))):
+        exp = orc.transform(orc.transform(v[k], R.c_to_mat(res[k].T_coarse)), R.c_to_mat(res[k].T_fine))
+        assert np.array_equal(t[lo:lo + len(v[k])].view(np.uint32), exp.view(np.uint32)), k

@@ -64,3 +64,35 @@ def test_missing_file_raises(tmp_path):
     exe = build(tmp_path)
     r = subprocess.run([exe, str(tmp_path / "nope.pcd"), str(tmp_path / "o")], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open" in r.stderr
+
+
+def test_ascii_file_with_unsigned_rgb_like_exampleTemp(tmp_path):
+    """examples/visualizer/exampleTemp.pcd declares `TYPE F F F U` and writes rgb as the packed unsigned integer
+    (e.g. 4281353262 = 0xFF30A42E); PCL stores those bits directly.  A reader that parses the token as a float value
+    yields wrong colours."""
+    exe = build(tmp_path)
+    rng = np.random.default_rng(6)
+    n = 10
+    xyz = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    rgba = rng.integers(0, 2 ** 24, n).astype(np.uint32) | np.uint32(0xFF000000)   # alpha 255: NaN patterns as floats
+    rgba[0] = 4281353262
+    lines = ["VERSION .7", "FIELDS x y z rgb", "SIZE 4 4 4 4", "TYPE F F F U", "COUNT 1 1 1 1", "WIDTH %d" % n, "HEIGHT 1",
+             "VIEWPOINT 0 0 0 1 0 0 0", "POINTS %d" % n, "DATA ascii"]
+    for p, c in zip(xyz, rgba):
+        lines.append("%.9g %.9g %.9g %d" % (p[0], p[1], p[2], int(c)))
+    src, dst = str(tmp_path / "u.pcd"), str(tmp_path / "u_bin.pcd")
+    open(src, "w").write("\n".join(lines) + "\n")
+    subprocess.run([exe, src, dst], capture_output=True, text=True, check=True)
+    back, w, h = gen_scene.read_pcd(dst)
+    assert np.array_equal(back["rgba"], rgba)
+    assert np.array_equal(back["x"], xyz[:, 0])
+
+
+def test_unsupported_headers_are_rejected(tmp_path):
+    exe = build(tmp_path)
+    hdr = ["VERSION .7", "FIELDS x y z rgb", "SIZE 8 8 8 4", "TYPE F F F U", "COUNT 1 1 1 1", "WIDTH 1", "HEIGHT 1",
+           "POINTS 1", "DATA ascii", "0 0 0 1"]
+    src = str(tmp_path / "bad.pcd")
+    open(src, "w").write("\n".join(hdr) + "\n")
+    r = subprocess.run([exe, src, str(tmp_path / "o.pcd")], capture_output=True, text=True)
+    assert r.returncode != 0 and "SIZE" in r.stderr
