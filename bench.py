@@ -304,12 +304,13 @@ def ndt_config2_leg(ctx, R, gen_scene, guess, hbm_peak):
     ctx.profile(False)
     ke, kc = ctx.profile_get("k_ndt_eval"), ctx.profile_get("k_ndt_control")
     kp = ctx.profile_get("k_ndt_persist")
+    kb = ctx.profile_get("ndt_voxel_build")
     ang2, tr2 = pose_err(r2[0]["T"], gen_scene.pairwise_gt(T2, 1))
     leg = {"workload": "configs[2]: edge-based NDT, one 1280x720 pair (921,600 points per frame), 0.05 m voxels, step 0.1, eps 0.01",
            "edge_points_src_tgt": [int(len(v2[1])), int(len(v2[0]))], "iterations": r2[0]["iterations"],
            "derivative_evals": r2[0]["n_derivative_evals"], "converged": bool(r2[0]["converged"]),
            "ms_align": ms2, "ms_per_ndt_iteration": ms2 / max(r2[0]["iterations"], 1),
-           "err_vs_ground_truth_rad_m": [ang2, tr2]}
+           "ms_voxel_build": kb["ms"], "err_vs_ground_truth_rad_m": [ang2, tr2]}
     evals = max(r2[0]["n_derivative_evals"] + r2[0]["n_hessian_evals"], 1)
     if kp["launches"]:
         leg["ms_per_derivative_eval"] = kp["ms"] / evals
@@ -414,7 +415,15 @@ def point_sharded_leg(ctx, R, gen_scene, torch, dist, rank, world, dev, a, hbm_p
     if world > 1:
         uid = torch.from_numpy(R.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
         dist.broadcast(uid, 0)
-        R.comm_init(ctx, world, rank, uid.cpu().numpy())
+        # (NCCL prints its version banner to stdout when the library creates its communicator: keep stdout = the JSON line)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            R.comm_init(ctx, world, rank, uid.cpu().numpy())
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     tgt = gen_scene.sample_room_surface(a.seed + 77, P)
     Tm = np.eye(4)
     Tm[:3, :3] = gen_scene.rot_axis([0.3, 1.0, 0.2], 0.0004)
@@ -442,6 +451,7 @@ def point_sharded_leg(ctx, R, gen_scene, torch, dist, rank, world, dev, a, hbm_p
     ms = ctx.timer_stop()
     ctx.profile(False)
     ks, kr, ka = ctx.profile_get("k_icp_stream"), ctx.profile_get("k_icp_rescan"), ctx.profile_get("allreduce")
+    kf = ctx.profile_get("k_icp_stream_first")
     ksol = ctx.profile_get("k_icp_solve")
     # the same align with the partial sums going through ncclAllReduce instead of the peer-memory exchange
     nccl_cmp = None
@@ -482,6 +492,7 @@ def point_sharded_leg(ctx, R, gen_scene, torch, dist, rank, world, dev, a, hbm_p
                "n_gpus": world, "iterations": int(res["iterations"]), "ms_total": ms_all,
                "ms_per_iteration": ms_all / max(res["iterations"], 1),
                "stream_kernel_ms_per_launch": ks["ms"] / max(ks["launches"], 1),
+               "first_iteration_full_query_ms": kf["ms"],
                "rescan_ms_per_launch": kr["ms"] / max(kr["launches"], 1),
                "exchange": ("one-shot peer-memory all-reduce over NVLink fused with the solve (k_icp_solve_peer)" if world > 1 and not ka["launches"]
                             else ("ncclAllReduce" if world > 1 else "none (1 GPU)")),

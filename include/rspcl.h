@@ -100,6 +100,13 @@ int rspcl_crop35(rspcl_ctx* ctx, const rspcl_cloud* in, rspcl_cloud* out);
 int rspcl_edge_extract(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_low, float t_high,
                        rspcl_cloud* out_edges, uint8_t* host_mask);
 
+/* The per-pixel label image of pcl::OrganizedEdgeFromRGBNormals::compute as edge_extractor.hpp:17-24 configures it
+ * (setDepthDisconThreshold(0.2), setMaxSearchNeighbors(50), all edge types), which rs-pcl --edges shows (main.cpp:58-74):
+ * bit 1 NAN_BOUNDARY, 2 OCCLUDING, 4 OCCLUDED (OrganizedEdgeBase, depth only), 16 RGB_CANNY.  The HIGH_CURVATURE class
+ * (bit 8: Canny on the integral-image normals, edge_extractor.hpp:10-15) is NOT computed.  host_labels: n_seg*w*h bytes. */
+int rspcl_edge_labels(rspcl_ctx* ctx, const rspcl_cloud* frames, float th_depth_discon, int max_search_neighbors,
+                      float t_low, float t_high, uint8_t* host_labels);
+
 /* pcl::ApproximateVoxelGrid::setLeafSize/setInputCloud/filter (icp:47,59-60,75-76; ndt:45,57-58,68-69;
  * incr:54-55).  Order- and bit-exact restatement of the 512-slot streaming filter.  in == out is allowed. */
 int rspcl_voxel_approx(rspcl_ctx* ctx, const rspcl_cloud* in, const float leaf[3], rspcl_cloud* out);
@@ -159,6 +166,11 @@ int rspcl_icp_align(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* t
  * align did not execute (earlier convergence) read -1. */
 int rspcl_icp_align_dump(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* tgt, const rspcl_icp_params* prm,
                          const float* guess, rspcl_icp_result* results, int n_dump_iterations, int32_t* host_corr);
+
+/* Host-only helper (no device work): the per-pair cluster sizes the persistent ICP kernel would use for one wave of
+ * pairs with `counts` source points, given `budget` SMs and the SMs a cluster of 1..8 CTAs occupies (`weights`, 8 entries,
+ * NULL: the cluster size itself).  Returns the number of source points a CTA keeps register-resident. */
+int rspcl_debug_plan_clusters(const int32_t* counts, int n, double budget, const double* weights, int32_t* out_cl);
 
 /* pcl::Registration::getFitnessScore(max_range) on an already transformed source: mean squared NN distance over
  * the source points whose NN is within max_range (squared distance <= max_range), DBL_MAX if none. */

@@ -35,6 +35,11 @@ int orc_canny(const OrcPoint* cloud, int w, int h, float t_low, float t_high,
 /* extract_edge_features: returns n, writes the RGB-Canny points (row-major order) and their pixel indices */
 int orc_extract_edges(const OrcPoint* cloud, int w, int h, float t_low, float t_high,
                       OrcPoint* out, int32_t* out_idx);
+/* pcl::OrganizedEdgeBase::extractEdges (features/impl/organized_edge_detection.hpp), as configured by
+ * edge_extractor.hpp:19-21 (setDepthDisconThreshold(0.2), setMaxSearchNeighbors(50)): per pixel label bits
+ * 1 = NAN_BOUNDARY, 2 = OCCLUDING, 4 = OCCLUDED from the depth (z) channel alone.  labels: w*h bytes. */
+void orc_depth_edge_labels(const OrcPoint* cloud, int w, int h, float th_depth_discon, int max_search_neighbors,
+                           uint8_t* labels);
 /* blur_filter.hpp:18-36 (centre 3/5 crop).  out holds (w*3/5)*(h*3/5) points; returns that count. */
 int orc_crop35(const OrcPoint* cloud, int w, int h, OrcPoint* out, int* out_w, int* out_h);
 

@@ -119,6 +119,14 @@ def extract_edges(cloud, w, h, t_low=40.0, t_high=100.0):
     return out[:n].copy(), idx[:n].copy()
 
 
+def depth_edge_labels(cloud, w, h, th_depth_discon=0.2, max_search_neighbors=50):
+    """OrganizedEdgeBase labels (1 NaN boundary, 2 occluding, 4 occluded) with edge_extractor.hpp:19-20's settings."""
+    cloud = pts(cloud)
+    lab = np.zeros(w * h, np.uint8)
+    lib().orc_depth_edge_labels(_p(cloud), w, h, C.c_float(th_depth_discon), int(max_search_neighbors), _p(lab))
+    return lab.reshape(h, w)
+
+
 def crop35(cloud, w, h):
     cloud = pts(cloud)
     out = np.zeros((w * 3 // 5) * (h * 3 // 5), POINT)

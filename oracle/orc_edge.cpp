@@ -11,6 +11,7 @@
 // Compile with -ffp-contract=off: PCL's header templates run as plain IEEE mul/add on x86-64.
 #include "orc.h"
 #include <cmath>
+#include <limits>
 #include <cfloat>
 #include <cstring>
 #include <vector>
@@ -166,6 +167,64 @@ extern "C" int orc_extract_edges(const OrcPoint* cloud, int w, int h, float t_lo
       ++n;
     }
   return n;
+}
+
+extern "C" void orc_depth_edge_labels(const OrcPoint* cloud, int w, int h, float th, int max_search, uint8_t* labels) {
+  // OrganizedEdgeBase<PointT, PointLT>::extractEdges: interior pixels only; eight neighbours in the order
+  // (-1,0) (-1,-1) (0,-1) (1,-1) (1,0) (1,1) (0,1) (-1,1) (dx, dy).  A finite pixel whose neighbours are all finite is
+  // labelled by the dominant (largest |.|) depth difference curr - neighbour against th * curr; a finite pixel next
+  // to non-finite ones searches across the hole in the mean direction of the invalid neighbours.
+  static const int DX[8] = {-1, -1, 0, 1, 1, 1, 0, -1}, DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+  for (int i = 0; i < w * h; ++i) labels[i] = 0;
+  for (int row = 1; row < h - 1; ++row)
+    for (int col = 1; col < w - 1; ++col) {
+      const int cur = row * w + col;
+      if (!std::isfinite(cloud[cur].z)) continue;
+      const float cd = std::fabs(cloud[cur].z);
+      float dist[8];
+      bool invalid = false;
+      for (int d = 0; d < 8; ++d) {
+        const float nz = cloud[cur + DY[d] * w + DX[d]].z;
+        if (!std::isfinite(nz)) {
+          invalid = true;
+          break;
+        }
+        dist[d] = cd - std::fabs(nz);
+      }
+      if (!invalid) {
+        float mn = dist[0], mx = dist[0];
+        for (int d = 1; d < 8; ++d) {
+          mn = dist[d] < mn ? dist[d] : mn;
+          mx = dist[d] > mx ? dist[d] : mx;
+        }
+        const float dom = std::fabs(mn) > std::fabs(mx) ? mn : mx;
+        if (std::fabs(dom) > th * std::fabs(cd)) labels[cur] |= dom > 0.f ? 4 : 2;  // OCCLUDED : OCCLUDING
+      } else {
+        int dx = 0, dy = 0, n_inv = 0;
+        for (int d = 0; d < 8; ++d)
+          if (!std::isfinite(cloud[cur + DY[d] * w + DX[d]].z)) {
+            dx += DX[d];
+            dy += DY[d];
+            ++n_inv;
+          }
+        const float fdx = float(dx) / float(n_inv), fdy = float(dy) / float(n_inv);
+        float corr = std::numeric_limits<float>::quiet_NaN();
+        for (int s = 1; s < max_search; ++s) {
+          const int sr = row + int(std::floor(fdy * float(s))), sc = col + int(std::floor(fdx * float(s)));
+          if (sr < 0 || sr >= h || sc < 0 || sc >= w) break;
+          if (std::isfinite(cloud[sr * w + sc].z)) {
+            corr = std::fabs(cloud[sr * w + sc].z);
+            break;
+          }
+        }
+        if (!std::isnan(corr)) {
+          const float dd = cd - corr;
+          if (std::fabs(dd) > th * std::fabs(cd)) labels[cur] |= dd > 0.f ? 4 : 2;
+        } else {
+          labels[cur] |= 1;  // NAN_BOUNDARY
+        }
+      }
+    }
 }
 
 extern "C" int orc_crop35(const OrcPoint* cloud, int w, int h, OrcPoint* out, int* out_w, int* out_h) {

@@ -151,17 +151,25 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
         bi[d] = clampi(r + d - 1, 0, h - 1) - (r0 - 2);
         bj[d] = clampi(c + d - 1, 0, w - 1) - (c0 - 2);
       }
-      const float sx[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};
-      const float sy[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};
-      float gx = 0.f, gy = 0.f;
-#pragma unroll
-      for (int kr = 0; kr < 3; ++kr)
-#pragma unroll
-        for (int kc = 0; kc < 3; ++kc) {
-          float v = s_blur[bi[kr]][bj[kc]];
-          gx = fadd(gx, fmul(sx[kr * 3 + kc], v));
-          gy = fadd(gy, fmul(sy[kr * 3 + kc], v));
-        }
+      // Sobel X {-1,0,1,-2,0,2,-1,0,1} and Y {-1,-2,-1,0,0,0,1,2,1} as the 9-tap correlations PCL runs, taps in row-major
+      // order from a zero accumulator.  The zero taps add +-0 to a finite sum (the blurred image is finite) and the +-1 /
+      // +-2 products are exact, so they are written as the adds and doublings they amount to: same bits, a third of
+      // the operations.
+      const float v00 = s_blur[bi[0]][bj[0]], v01 = s_blur[bi[0]][bj[1]], v02 = s_blur[bi[0]][bj[2]];
+      const float v10 = s_blur[bi[1]][bj[0]], v12 = s_blur[bi[1]][bj[2]];
+      const float v20 = s_blur[bi[2]][bj[0]], v21 = s_blur[bi[2]][bj[1]], v22 = s_blur[bi[2]][bj[2]];
+      float gx = fadd(0.f, -v00);
+      gx = fadd(gx, v02);
+      gx = fadd(gx, -fadd(v10, v10));
+      gx = fadd(gx, fadd(v12, v12));
+      gx = fadd(gx, -v20);
+      gx = fadd(gx, v22);
+      float gy = fadd(0.f, -v00);
+      gy = fadd(gy, -fadd(v01, v01));
+      gy = fadd(gy, -v02);
+      gy = fadd(gy, v20);
+      gy = fadd(gy, fadd(v21, v21));
+      gy = fadd(gy, v22);
       m = __fsqrt_rn(fadd(fmul(gx, gx), fmul(gy, gy)));
       // the direction is only ever read for centre pixels that pass the low threshold (suppressNonMaxima)
       if (i >= 1 && i <= TH && j >= 1 && j <= TW) s_dir[i - 1][j - 1] = !(m < t_low) ? (uint8_t)direction_bin_fast(gy, gx) : (uint8_t)255;
@@ -268,6 +276,74 @@ __global__ void k_uf_flag(const uint8_t* __restrict__ cls, int* __restrict__ par
     if (c[i] == 2) strong[(size_t)seg * stride + uf_find(par, i)] = 1;
 }
 
+// pcl::OrganizedEdgeBase::extractEdges: NaN-boundary / occluding / occluded labels from the depth channel (the classes
+// edge_extractor.hpp:26-34 gathers next to the RGB edges; one thread per interior pixel, the 3x3 neighbourhood is L1/L2
+// traffic).  label |= 1 NAN_BOUNDARY, 2 OCCLUDING, 4 OCCLUDED.
+__global__ void k_depth_edges(const float4* __restrict__ pts, int w, int h, int stride, float th, int max_search,
+                              uint8_t* __restrict__ labels) {
+  const int seg = blockIdx.y;
+  const float4* P = pts + (size_t)seg * stride;
+  uint8_t* L = labels + (size_t)seg * stride;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < w * h; idx += gridDim.x * blockDim.x) {
+    const int row = idx / w, col = idx - row * w;
+    uint8_t lab = 0;
+    if (row >= 1 && row < h - 1 && col >= 1 && col < w - 1) {
+      const float z = P[idx].z;
+      if (isfinite(z)) {
+        const float cd = fabsf(z);
+        const int DX[8] = {-1, -1, 0, 1, 1, 1, 0, -1}, DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+        float nz[8];
+        int dx = 0, dy = 0, n_inv = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          nz[d] = P[idx + DY[d] * w + DX[d]].z;
+          if (!isfinite(nz[d])) {
+            dx += DX[d];
+            dy += DY[d];
+            ++n_inv;
+          }
+        }
+        float mn = __fsub_rn(cd, fabsf(nz[0])), mx = mn;  // (only used when every neighbour is finite)
+#pragma unroll
+        for (int d = 1; d < 8; ++d) {
+          const float dd = __fsub_rn(cd, fabsf(nz[d]));
+          mn = dd < mn ? dd : mn;
+          mx = dd > mx ? dd : mx;
+        }
+        if (n_inv == 0) {
+          const float dom = fabsf(mn) > fabsf(mx) ? mn : mx;
+          if (fabsf(dom) > fmul(th, cd)) lab |= dom > 0.f ? 4 : 2;
+        } else {
+          const float fdx = __fdiv_rn((float)dx, (float)n_inv), fdy = __fdiv_rn((float)dy, (float)n_inv);
+          float corr = NAN;
+          for (int s = 1; s < max_search; ++s) {
+            const int sr = row + (int)floorf(fmul(fdy, (float)s)), sc = col + (int)floorf(fmul(fdx, (float)s));
+            if (sr < 0 || sr >= h || sc < 0 || sc >= w) break;
+            const float sz = P[sr * w + sc].z;
+            if (isfinite(sz)) {
+              corr = fabsf(sz);
+              break;
+            }
+          }
+          if (!isnan(corr)) {
+            const float dd = __fsub_rn(cd, corr);
+            if (fabsf(dd) > fmul(th, cd)) lab |= dd > 0.f ? 4 : 2;
+          } else {
+            lab |= 1;
+          }
+        }
+      }
+    }
+    L[idx] = lab;
+  }
+}
+
+__global__ void k_or_mask(const uint8_t* __restrict__ mask, uint8_t* __restrict__ labels, int n, int stride) {
+  const int seg = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (mask[(size_t)seg * stride + i]) labels[(size_t)seg * stride + i] |= 16;  // EDGELABEL_RGB_CANNY
+}
+
 constexpr int CB = 1024;  // pixels per compaction block
 
 // mask = candidate whose component holds a strong pixel; per-block edge counts for the ordered compaction
@@ -364,8 +440,41 @@ __global__ void __launch_bounds__(CB) k_scatter(const uint8_t* __restrict__ mask
 
 }  // namespace
 
+static int edge_extract_impl(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_low, float t_high, rspcl_cloud* out_edges,
+                             uint8_t* host_mask, uint8_t* d_labels_or);
+
 extern "C" int rspcl_edge_extract(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_low, float t_high,
                                   rspcl_cloud* out_edges, uint8_t* host_mask) {
+  return edge_extract_impl(ctx, frames, t_low, t_high, out_edges, host_mask, nullptr);
+}
+
+// pcl::OrganizedEdgeFromRGBNormals::compute as edge_extractor.hpp:17-24 configures it, minus the HIGH_CURVATURE class (which
+// needs the integral-image normals): per pixel label = 1 NAN_BOUNDARY | 2 OCCLUDING | 4 OCCLUDED | 16 RGB_CANNY.
+extern "C" int rspcl_edge_labels(rspcl_ctx* ctx, const rspcl_cloud* frames, float th_depth_discon, int max_search_neighbors,
+                                 float t_low, float t_high, uint8_t* host_labels) {
+  if (!ctx || !frames || !host_labels) return RSPCL_ERR_ARG;
+  if (frames->height <= 0 || frames->width <= 0) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "edge_labels: input is not organized");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int w = frames->width, h = frames->height, n = w * h, S = frames->n_seg;
+  Scratch scr(ctx);
+  uint8_t* d_lab = nullptr;
+  CU(ctx, scr.alloc(&d_lab, (size_t)S * frames->stride));
+  dim3 g(blocks_per_seg(ctx, S, n, 256), S);
+  k_depth_edges<<<g, 256, 0, ctx->stream>>>(frames->pts, w, h, frames->stride, th_depth_discon, max_search_neighbors, d_lab);
+  LAUNCH_CHECK(ctx);
+  TmpCloud E(ctx);
+  int rc = E.init(S, n);
+  if (rc) RSPCL_FAIL(ctx, rc, "edge_labels: scratch allocation failed");
+  rc = edge_extract_impl(ctx, frames, t_low, t_high, &E.c, nullptr, d_lab);
+  if (rc) return rc;
+  for (int s = 0; s < S; ++s) CU(ctx, small_d2h(ctx, host_labels + (size_t)s * n, d_lab + (size_t)s * frames->stride, n));
+  CU(ctx, ctx_sync(ctx));
+  scr.ok();
+  return RSPCL_OK;
+}
+
+static int edge_extract_impl(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_low, float t_high, rspcl_cloud* out_edges,
+                             uint8_t* host_mask, uint8_t* d_labels_or) {
   if (!ctx || !frames || !out_edges || frames == out_edges) return RSPCL_ERR_ARG;
   if (frames->height <= 0 || frames->width <= 0) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "edge_extract: input is not organized");
   if (out_edges->n_seg != frames->n_seg) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "edge_extract: output n_seg mismatch");
@@ -408,6 +517,10 @@ extern "C" int rspcl_edge_extract(rspcl_ctx* ctx, const rspcl_cloud* frames, flo
   LAUNCH_CHECK(ctx);
   out_edges->width = out_edges->height = 0;
   out_edges->max_count_hint = out_edges->stride < n ? out_edges->stride : n;
+  if (d_labels_or) {
+    k_or_mask<<<g2, 256, 0, ctx->stream>>>(mask, d_labels_or, n, stride);
+    LAUNCH_CHECK(ctx);
+  }
 
   int over = 0;
   if (host_mask) {

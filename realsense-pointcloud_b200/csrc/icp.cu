@@ -578,55 +578,95 @@ __global__ void __launch_bounds__(IT) k_icp_step(float4* __restrict__ work, cons
 }
 
 // point-sharded mode: CTA partials -> per-pair totals (then all-reduced across ranks before the solve)
-__global__ void k_icp_sum_partials(const double* __restrict__ partials, int nblk, const IcpState* __restrict__ st,
-                                   double* __restrict__ totals) {
-  const int seg = blockIdx.x, lane = threadIdx.x;
-  if (lane >= NRED) return;
-  double v = 0;
-  // finished pairs contribute zeros on every rank (their k_icp_step exits early and leaves stale partials)
-  if (!st[seg].done) {
-    const double* P = partials + (size_t)seg * nblk * NRED + lane;
-    for (int b = 0; b < nblk; ++b) v += P[(size_t)b * NRED];
-  }
-  totals[seg * NRED + lane] = v;
-}
+__global__ void __launch_bounds__(256) k_icp_sum_partials(const double* __restrict__ partials, int nblk, const IcpState* __restrict__ st,
+                                                          double* __restrict__ totals);
 
 // K5b: one warp per pair combines the CTA partials in block order (deterministic) and runs the solve
-__global__ void __launch_bounds__(32) k_icp_solve(IcpState* __restrict__ st, const double* __restrict__ partials, int nblk,
-                                                  IcpDevParams prm, int* __restrict__ n_active) {
+// Sum of the CTA partials of one pair in a FIXED order: the 256 threads form 8 groups of 32 lanes, lane k < 17 of group g
+// adds value k of blocks g, g + 8, g + 16, ... (coalesced 136-byte rows, four independent chains), the 8 group totals are
+// then added in group order -- reproducible run to run.  (One warp summing thousands of partials serially cost 170 us
+// per iteration on a 50 M-point pair.)
+constexpr int SOLVE_T = 256;
+__device__ __forceinline__ void icp_combine_partials(const double* __restrict__ P /* [nblk][NRED] */, int nblk, double* s_tmp /* [SOLVE_T] */,
+                                                     double* sums /* [NRED] */) {
+  const int k = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  constexpr int NG = SOLVE_T / 32;
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+  if (k < NRED) {
+    int b = grp;
+    for (; b + 3 * NG < nblk; b += 4 * NG) {
+      v0 += P[(size_t)b * NRED + k];
+      v1 += P[(size_t)(b + NG) * NRED + k];
+      v2 += P[(size_t)(b + 2 * NG) * NRED + k];
+      v3 += P[(size_t)(b + 3 * NG) * NRED + k];
+    }
+    for (; b < nblk; b += NG) v0 += P[(size_t)b * NRED + k];
+  }
+  s_tmp[threadIdx.x] = (v0 + v1) + (v2 + v3);
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double t = 0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) t += s_tmp[g * 32 + threadIdx.x];
+    sums[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_icp_sum_partials(const double* __restrict__ partials, int nblk, const IcpState* __restrict__ st,
+                                                          double* __restrict__ totals) {
+  const int seg = blockIdx.x;
+  __shared__ double sums[NRED];
+  __shared__ double s_tmp[SOLVE_T];
+  // finished pairs contribute zeros on every rank (their kernels exit early and leave stale partials)
+  if (st[seg].done) {
+    if (threadIdx.x < NRED) totals[seg * NRED + threadIdx.x] = 0.0;
+    return;
+  }
+  icp_combine_partials(partials + (size_t)seg * nblk * NRED, nblk, s_tmp, sums);
+  if (threadIdx.x < NRED) totals[seg * NRED + threadIdx.x] = sums[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SOLVE_T) k_icp_solve(IcpState* __restrict__ st, const double* __restrict__ partials, int nblk,
+                                                       IcpDevParams prm, int* __restrict__ n_active) {
   const int seg = blockIdx.x;
   if (st[seg].done) return;
-  const int lane = threadIdx.x;
   __shared__ double sums[NRED];
-  if (lane < NRED) {
-    double v = 0;
-    const double* P = partials + (size_t)seg * nblk * NRED + lane;
-    for (int b = 0; b < nblk; ++b) v += P[(size_t)b * NRED];
-    sums[lane] = v;
+  __shared__ double s_tmp[SOLVE_T];
+  if (nblk <= 64) {  // few CTAs per pair (batches of small pairs): one warp's serial sum is the shortest path
+    if (threadIdx.x < NRED) {
+      double v = 0;
+      const double* P = partials + (size_t)seg * nblk * NRED + threadIdx.x;
+      for (int b = 0; b < nblk; ++b) v += P[(size_t)b * NRED];
+      sums[threadIdx.x] = v;
+    }
+    __syncthreads();
+  } else {
+    icp_combine_partials(partials + (size_t)seg * nblk * NRED, nblk, s_tmp, sums);
   }
-  __syncwarp();
-  icp_solve_pair(&st[seg], sums, prm, n_active, lane);
+  if (threadIdx.x < 32) icp_solve_pair(&st[seg], sums, prm, n_active, threadIdx.x);
 }
 
 // point-sharded mode, peer-memory path: the same warp combines this rank's CTA partials, exchanges the 17 totals with every
 // other rank through NVLink peer memory (one-shot all-reduce, comm.cu / common.cuh) and runs the solve -- one launch instead
 // of {sum partials, ncclAllReduce, solve}.  Every rank sums the ranks' totals in rank order: identical bits, identical
 // convergence decisions, no broadcast.
-__global__ void __launch_bounds__(32) k_icp_solve_peer(IcpState* __restrict__ st, const double* __restrict__ partials, int nblk,
-                                                       IcpDevParams prm, int* __restrict__ n_active, PeerX X) {
+__global__ void __launch_bounds__(SOLVE_T) k_icp_solve_peer(IcpState* __restrict__ st, const double* __restrict__ partials, int nblk,
+                                                            IcpDevParams prm, int* __restrict__ n_active, PeerX X) {
   const int seg = blockIdx.x;
   if (st[seg].done) return;  // (identical on every rank)
-  const int lane = threadIdx.x;
   __shared__ double sums[NRED];
-  double v = 0;
-  if (lane < NRED) {
-    const double* P = partials + (size_t)seg * nblk * NRED + lane;
-    for (int b = 0; b < nblk; ++b) v += P[(size_t)b * NRED];
+  __shared__ double s_tmp[SOLVE_T];
+  icp_combine_partials(partials + (size_t)seg * nblk * NRED, nblk, s_tmp, sums);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    double v = lane < NRED ? sums[lane] : 0.0;
+    v = peer_allreduce_warp(X, v, lane, NRED, seg);
+    __syncwarp();
+    if (lane < NRED) sums[lane] = v;
+    __syncwarp();
+    icp_solve_pair(&st[seg], sums, prm, n_active, lane);
   }
-  v = peer_allreduce_warp(X, v, lane, NRED, seg);
-  if (lane < NRED) sums[lane] = v;
-  __syncwarp();
-  icp_solve_pair(&st[seg], sums, prm, n_active, lane);
 }
 
 __global__ void k_copy_work(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
@@ -697,12 +737,14 @@ __global__ void k_pack_i32(const int* __restrict__ v, const int* __restrict__ co
 // Certified-cache correspondence passes for clouds that do not fit the shared-memory kernel (global-memory grid).
 // Per source point: ci = position of its cached match inside g.sorted (-1: none), lb = lower bound of the true distance
 // to every OTHER target point (to every target point if ci < 0).  See icp_persist.cuh for why this is exact.
-//   k_icp_stream  one streaming pass over the working cloud: move the point, decay its bound by the distance moved,
-//                 re-measure the cached match (one 16 B gather, spatially coherent because source and g.sorted are both
-//                 in cell order) and, if the bound still decides, accumulate the 17 sums.  Points whose bound no longer
-//                 decides are appended to the block's slice of a work list IN POINT ORDER (ballot + prefix counts), so
-//                 every later sum is taken in a fixed order and results stay reproducible run to run.
-//                 Bytes per point: 16 R + 4 R (lb) + 4 R (ci) + 16 R (match) + 16 W + 4 W = 60 (algorithmic: 32).
+//   k_icp_stream  one streaming pass over the working cloud, which is a pair of 16-byte records per point:
+//                 A = {x, y, z, certified bound} (rewritten every iteration) and B = {matched target x, y, z, its position
+//                 in g.sorted} (rewritten only by a re-query).  Move the point, decay its bound by the distance moved,
+//                 re-measure the cached match FROM THE RECORD (no gather into the target: round 1 paid a 32-byte sector
+//                 for every 16-byte match) and, if the bound still decides, accumulate the 17 sums.  Points whose bound
+//                 no longer decides are appended to the block's slice of a work list IN POINT ORDER (ballot + prefix
+//                 counts), so every later sum is taken in a fixed order and results stay reproducible run to run.
+//                 Bytes per point: 32 R + 16 W = 48, all streaming (algorithmic: 32).
 //   k_icp_rescan  re-queries the listed points in the voxel-hash grid (exact NN inside the gate ball, second-best
 //                 distance for the new bound) and adds its own partial sums.  The block slices are concatenated through
 //                 an exclusive scan of their counts (k_wl_offsets), item t always goes to the same thread.
@@ -768,12 +810,13 @@ __device__ __forceinline__ int icp_requery(const DevGrid& g, int seg, const floa
 template <bool FIRST>  // FIRST: nothing is cached yet (iteration 0), every point is queried in place (no work list)
 __global__ void __launch_bounds__(IT) k_icp_stream(float4* __restrict__ work, const int* __restrict__ count, int stride,
                                                    const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
-                                                   float* __restrict__ lb, int* __restrict__ ci,
+                                                   float4* __restrict__ recB, const int* __restrict__ perm, int pstride,
                                                    int* __restrict__ wl, int* __restrict__ wlcount,
                                                    double* __restrict__ partials, int* __restrict__ corr_out, int corr_iters) {
   __shared__ float M[16];
   __shared__ double s_red[IT / 32][NRED];
-  __shared__ int s_wcnt[2][IT / 32];
+  constexpr int SU = 4;  // tiles in flight per thread in the streaming pass (memory-level parallelism: 2 x SU 16-byte loads)
+  __shared__ int s_wcnt[2][SU][IT / 32];
   const int seg = blockIdx.y;
   if (st[seg].done) return;
   const int n = count[seg];
@@ -790,14 +833,93 @@ __global__ void __launch_bounds__(IT) k_icp_stream(float4* __restrict__ work, co
   const int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
   const float r = prm.search_r;
   int nlist = 0, par = 0;
-  for (int base = lo; base < hi; base += IT, par ^= 1) {  // block-uniform trip count
+  if (!FIRST) {
+    // Steady-state pass: SU tiles per trip -- all 2 x SU record loads of a thread are issued before the first is consumed
+    // (the pass is bound by load latency at this occupancy, not by bytes), one barrier per SU tiles.
+    for (int base = lo; base < hi; base += SU * IT, par ^= 1) {  // block-uniform trip count
+      float4 pA[SU], pB[SU];
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const int i = base + u * IT + threadIdx.x;
+        if (i < hi) {
+          pA[u] = work[(size_t)seg * stride + i];
+          pB[u] = recB[(size_t)seg * stride + i];
+        } else {
+          pA[u] = make_float4(NAN, NAN, NAN, 0.f);
+          pB[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        }
+      }
+      unsigned fbits = 0u;
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const int i = base + u * IT + threadIdx.x;
+        if (i >= hi) continue;
+        const size_t gi = (size_t)seg * stride + i;
+        float4 p = pA[u];
+        float lbv = p.w;
+        const bool fin = finite3(p.x, p.y, p.z);
+        const int orig = want_corr ? perm[(size_t)seg * pstride + i] : 0;  // original source index (dump only)
+        if (!fin) {
+          if (want_corr) first_corr[(size_t)seg * stride + orig] = -1;
+          continue;
+        }
+        if (apply) {
+          const float3 q = xform_point(M, p.x, p.y, p.z);
+          lbv = lbv - __fmaf_rn(sqrt_approx(dist2_l2simple(q.x, q.y, q.z, p.x, p.y, p.z)), 1.00001f, 1e-9f);
+          p.x = q.x;
+          p.y = q.y;
+          p.z = q.z;
+          p.w = lbv;
+          work[gi] = p;
+        }
+        const float4 t = pB[u];  // record B: the cached match and where it lives in g.sorted
+        const int c = __float_as_int(t.w);
+        bool valid;
+        float bd = INFINITY;
+        if (c >= 0) {
+          bd = dist2_l2simple(p.x, p.y, p.z, t.x, t.y, t.z);
+          valid = __fmaf_rn(sqrt_approx(bd), 1.0001f, 1e-7f) < lbv;
+        } else {
+          valid = lbv > r;
+        }
+        if (!valid) {
+          fbits |= 1u << u;
+        } else {
+          const bool ok = c >= 0 && !((double)bd > prm.max_dist_sqr);
+          if (want_corr) first_corr[(size_t)seg * stride + orig] = ok ? __float_as_int(__ldg(&g.sorted[c]).w) : -1;
+          if (ok) icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
+        }
+      }
+      // ordered compaction of the flagged points of these SU tiles (ascending point index: tile, warp, lane)
+      unsigned bal[SU];
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        bal[u] = __ballot_sync(0xffffffffu, (fbits >> u) & 1u);
+        if (lane == 0) s_wcnt[par][u][wid] = __popc(bal[u]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < IT / 32; ++w) {
+          const int cw = s_wcnt[par][u][w];
+          before += (w < wid) ? cw : 0;
+          total += cw;
+        }
+        if ((fbits >> u) & 1u)
+          wl[(size_t)seg * stride + lo + nlist + before + __popc(bal[u] & ((1u << lane) - 1u))] = base + u * IT + threadIdx.x;
+        nlist += total;
+      }
+    }
+  }
+  for (int base = lo; FIRST && base < hi; base += IT, par ^= 1) {  // first iteration: every point is queried in place
     const int i = base + threadIdx.x;
     bool flag = false;
     if (i < hi) {
       const size_t gi = (size_t)seg * stride + i;
-      float4 p = work[gi];
-      float lbv = lb[gi];
-      const int c = ci[gi];
+      float4 p = work[gi];  // record A: position + certified bound
+      float lbv = p.w;
       const bool fin = finite3(p.x, p.y, p.z);
       if (apply && fin) {
         const float3 q = xform_point(M, p.x, p.y, p.z);
@@ -805,28 +927,34 @@ __global__ void __launch_bounds__(IT) k_icp_stream(float4* __restrict__ work, co
         p.x = q.x;
         p.y = q.y;
         p.z = q.z;
-        work[gi] = p;
       }
-      if (!FIRST) lb[gi] = lbv;
+      const int orig = want_corr ? perm[(size_t)seg * pstride + i] : 0;  // original source index (dump only)
       if (!fin) {
-        if (want_corr) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = -1;
-        if (FIRST) lb[gi] = 0.f;
+        if (want_corr) first_corr[(size_t)seg * stride + orig] = -1;
+        if (FIRST) {
+          p.w = 0.f;
+          work[gi] = p;
+          recB[gi] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        }
       } else if (FIRST) {
         float bd, lbn;
         int pos;
         float4 t;
         const int best = icp_requery(g, seg, p, -1, r, &bd, &pos, &t, &lbn);
-        lb[gi] = lbn;
-        ci[gi] = pos;
+        p.w = lbn;
+        work[gi] = p;
+        recB[gi] = make_float4(t.x, t.y, t.z, __int_as_float(pos));
         const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
-        if (want_corr) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = ok ? best : -1;
+        if (want_corr) first_corr[(size_t)seg * stride + orig] = ok ? best : -1;
         if (ok) icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
       } else {
+        const float4 t = recB[gi];  // record B: the cached match and where it lives in g.sorted
+        const int c = __float_as_int(t.w);
+        p.w = lbv;
+        work[gi] = p;
         bool valid;
         float bd = INFINITY;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c >= 0) {
-          t = __ldg(&g.sorted[c]);
           bd = dist2_l2simple(p.x, p.y, p.z, t.x, t.y, t.z);
           valid = __fmaf_rn(sqrt_approx(bd), 1.0001f, 1e-7f) < lbv;
         } else {
@@ -836,24 +964,13 @@ __global__ void __launch_bounds__(IT) k_icp_stream(float4* __restrict__ work, co
           flag = true;
         } else {
           const bool ok = c >= 0 && !((double)bd > prm.max_dist_sqr);
-          if (want_corr) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = ok ? __float_as_int(t.w) : -1;
+          if (want_corr) first_corr[(size_t)seg * stride + orig] = ok ? __float_as_int(__ldg(&g.sorted[c]).w) : -1;
           if (ok) icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
         }
       }
     }
-    // ordered compaction of the flagged points of this tile
-    const unsigned bal = __ballot_sync(0xffffffffu, flag);
-    if (lane == 0) s_wcnt[par][wid] = __popc(bal);
-    __syncthreads();
-    int before = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < IT / 32; ++w) {
-      const int cw = s_wcnt[par][w];
-      before += (w < wid) ? cw : 0;
-      total += cw;
-    }
-    if (flag) wl[(size_t)seg * stride + lo + nlist + before + __popc(bal & ((1u << lane) - 1u))] = i;
-    nlist += total;
+    // (nothing is flagged in the first iteration: the work list stays empty)
+    (void)flag;
   }
   if (threadIdx.x == 0) wlcount[seg * gridDim.x + blockIdx.x] = nlist;
 #pragma unroll
@@ -912,7 +1029,7 @@ __global__ void __launch_bounds__(1024) k_wl_offsets(const int* __restrict__ wlc
 
 __global__ void __launch_bounds__(IT) k_icp_rescan(float4* __restrict__ work, const int* __restrict__ count, int stride,
                                                    const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
-                                                   float* __restrict__ lb, int* __restrict__ ci,
+                                                   float4* __restrict__ recB, const int* __restrict__ perm, int pstride,
                                                    const int* __restrict__ wl, const int* __restrict__ wloff,
                                                    double* __restrict__ partials, int* __restrict__ corr_out, int corr_iters) {
   __shared__ double s_red[IT / 32][NRED];
@@ -943,11 +1060,11 @@ __global__ void __launch_bounds__(IT) k_icp_rescan(float4* __restrict__ work, co
     float bd, lbn;
     int pos;
     float4 t;
-    const int best = icp_requery(g, seg, p, ci[gi], r, &bd, &pos, &t, &lbn);
-    lb[gi] = lbn;
-    ci[gi] = pos;
+    const int best = icp_requery(g, seg, p, __float_as_int(recB[gi].w), r, &bd, &pos, &t, &lbn);
+    work[gi].w = lbn;
+    recB[gi] = make_float4(t.x, t.y, t.z, __int_as_float(pos));
     const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
-    if (want_corr) first_corr[(size_t)seg * stride + __float_as_int(p.w)] = ok ? best : -1;
+    if (want_corr) first_corr[(size_t)seg * stride + perm[(size_t)seg * pstride + i]] = ok ? best : -1;
     if (ok) icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
   }
 #pragma unroll
@@ -1080,8 +1197,8 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   const char* cache_env = getenv("RSPCL_ICP_CACHE");
   const bool use_cache = !brute && !(cache_env && cache_env[0] == '0');
   const int nblk_total = use_cache ? 2 * nblk : nblk;
-  float* g_lb = nullptr;
-  int *g_ci = nullptr, *g_wl = nullptr, *g_wlcount = nullptr, *g_wloff = nullptr;
+  float4* g_rb = nullptr;  // record B of every source point (cached match)
+  int *g_wl = nullptr, *g_wlcount = nullptr, *g_wloff = nullptr;
   CU(ctx, scr.alloc(&partials, (size_t)S * nblk_total * NRED));
   CU(ctx, scr.alloc(&d_prev, (size_t)S));
   CU(ctx, scr.alloc(&n_active, 1));
@@ -1405,13 +1522,10 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   int done_iters = 0, chunk = 1, active = persist_done ? 0 : active_init;
   if (use_cache && !persist_done) {
     const size_t np = (size_t)S * wstride;
-    CU(ctx, scr.alloc(&g_lb, np));
-    CU(ctx, scr.alloc(&g_ci, np));
+    CU(ctx, scr.alloc(&g_rb, np));
     CU(ctx, scr.alloc(&g_wl, np));
     CU(ctx, scr.alloc(&g_wlcount, (size_t)S * nblk));
     CU(ctx, scr.alloc(&g_wloff, (size_t)S * (nblk + 1)));
-    CU(ctx, cudaMemsetAsync(g_lb, 0, np * sizeof(float), ctx->stream));
-    CU(ctx, cudaMemsetAsync(g_ci, 0xFF, np * sizeof(int), ctx->stream));
   }
   double prof_units = 0;  // source points per launch (all pairs; converged pairs exit early)
   if (ctx->prof_on && !persist_done) {
@@ -1435,29 +1549,29 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       }
       if (use_cache) {
         {
-          ProfScope prof(ctx, "k_icp_stream", prof_units);
+          ProfScope prof(ctx, (done_iters == 0 && k == 0) ? "k_icp_stream_first" : "k_icp_stream", prof_units);
           if (done_iters == 0 && k == 0)
-            k_icp_stream<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wlcount,
+            k_icp_stream<true><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_rb, perm, pstride, g_wl, g_wlcount,
                                                               partials, d_first_corr, corr_iters);
           else
-            k_icp_stream<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wlcount,
+            k_icp_stream<false><<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_rb, perm, pstride, g_wl, g_wlcount,
                                                                partials, d_first_corr, corr_iters);
           LAUNCH_CHECK(ctx);
         }
         ProfScope prof(ctx, "k_icp_rescan", prof_units);
         k_wl_offsets<<<S, 1024, 0, ctx->stream>>>(g_wlcount, nblk, st, g_wloff);
         LAUNCH_CHECK(ctx);
-        k_icp_rescan<<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_lb, g_ci, g_wl, g_wloff,
+        k_icp_rescan<<<gstep, IT, 0, ctx->stream>>>(work, src->count, wstride, st, g, dp, g_rb, perm, pstride, g_wl, g_wloff,
                                                     partials, d_first_corr, corr_iters);
         LAUNCH_CHECK(ctx);
       }
       ProfScope prof2(ctx, "k_icp_solve", (double)S);
       if (sharded && comm_peer_ready(ctx, S, NRED)) {
         // partial sums of this rank's shard -> one-shot exchange through peer memory, fused with the solve
-        k_icp_solve_peer<<<S, 32, 0, ctx->stream>>>(st, partials, nblk_total, dp, n_active, comm_peer_next(ctx));
+        k_icp_solve_peer<<<S, SOLVE_T, 0, ctx->stream>>>(st, partials, nblk_total, dp, n_active, comm_peer_next(ctx));
       } else if (sharded) {
         // partial sums of this rank's shard -> ncclAllReduce -> identical solve on every rank
-        k_icp_sum_partials<<<S, 32, 0, ctx->stream>>>(partials, nblk_total, st, totals);
+        k_icp_sum_partials<<<S, SOLVE_T, 0, ctx->stream>>>(partials, nblk_total, st, totals);
         LAUNCH_CHECK(ctx);
         int rcc;
         {
@@ -1465,9 +1579,9 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
           rcc = comm_allreduce_f64(ctx, totals, (size_t)S * NRED);
         }
         if (rcc) return rcc;
-        k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, totals, 1, dp, n_active);
+        k_icp_solve<<<S, SOLVE_T, 0, ctx->stream>>>(st, totals, 1, dp, n_active);
       } else {
-        k_icp_solve<<<S, 32, 0, ctx->stream>>>(st, partials, nblk_total, dp, n_active);
+        k_icp_solve<<<S, SOLVE_T, 0, ctx->stream>>>(st, partials, nblk_total, dp, n_active);
       }
       LAUNCH_CHECK(ctx);
     }
@@ -1623,6 +1737,18 @@ extern "C" int rspcl_icp_align_dump(rspcl_ctx* ctx, const rspcl_cloud* src, cons
                                     const float* guess, rspcl_icp_result* results, int n_dump_iterations, int32_t* host_corr) {
   if (!host_corr) return RSPCL_ERR_ARG;
   return icp_align_host(ctx, src, tgt, prm, guess, results, nullptr, n_dump_iterations, host_corr);
+}
+
+// Host-only: the cluster-size plan of the persistent ICP kernel for one wave of pairs (exported for the CPU test-suite;
+// weights = SMs a cluster of c CTAs occupies, c = 1..8, nullptr: c itself).  Returns the resident-slice capacity.
+extern "C" int rspcl_debug_plan_clusters(const int32_t* counts, int n, double budget, const double* weights, int32_t* out_cl) {
+  if (!counts || !out_cl || n < 0) return -1;
+  double w[P_CLMAX + 1];
+  for (int c = 0; c <= P_CLMAX; ++c) w[c] = weights ? (c ? weights[c - 1] : 0.0) : (double)c;
+  std::vector<int> cnt(counts, counts + n), cl;
+  plan_clusters(cnt, budget, w, &cl);
+  for (int i = 0; i < n; ++i) out_cl[i] = cl[i];
+  return P_CHUNK;
 }
 
 extern "C" int rspcl_icp_align_sharded(rspcl_ctx* ctx, const rspcl_cloud* src_shard, const rspcl_cloud* tgt,

@@ -297,8 +297,10 @@ __device__ __forceinline__ double xCh(const double* xr, const double* C, const d
 // One source point against its 3x3x3 voxel neighbourhood: computeDerivatives' loop body (transform, radiusSearch over the
 // voxel centroids, updateDerivatives / updateHessian).  Shared by the per-evaluation kernel and the persistent kernel.
 // n_pairs counts the (point, voxel) pairs that contributed (roofline accounting).
+// LISTED: the (point, voxel) pair was already found by a candidate pass (k_ndt_persist), `listed_vi` is its voxel.
+template <bool LISTED>
 __device__ __forceinline__ void ndt_point_eval(const float4 p, const NdtEval& E, const NdtGridDev& G, int tseg, bool wantH,
-                                               double d1, double d2, double* acc, int& n_pairs) {
+                                               double d1, double d2, double* acc, int& n_pairs, int listed_vi = -1) {
   do {
     if (!finite3(p.x, p.y, p.z)) break;
     const float3 xt = xform_point(E.T, p.x, p.y, p.z);
@@ -320,16 +322,18 @@ __device__ __forceinline__ void ndt_point_eval(const float4 p, const NdtEval& E,
       he[0] = dot3(x, E.ha[9]); he[1] = dot3(x, E.ha[10]); he[2] = dot3(x, E.ha[11]);
       hf[0] = dot3(x, E.ha[12]); hf[1] = dot3(x, E.ha[13]); hf[2] = dot3(x, E.ha[14]);
     }
-    for (int dz = -1; dz <= 1; ++dz)
-      for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int vi = ndt_lookup(G, ndt_key(tseg, cx + dx, cy + dy, cz + dz));
+    for (int dz = -1; dz <= (LISTED ? -1 : 1); ++dz)
+      for (int dy = -1; dy <= (LISTED ? -1 : 1); ++dy)
+        for (int dx = -1; dx <= (LISTED ? -1 : 1); ++dx) {
+          const int vi = LISTED ? listed_vi : ndt_lookup(G, ndt_key(tseg, cx + dx, cy + dy, cz + dz));
           if (vi < 0) continue;
           const VoxRec* V = &G.vox[vi];
-          const float ddx = __fsub_rn(xt.x, V->centroid[0]), ddy = __fsub_rn(xt.y, V->centroid[1]),
-                      ddz = __fsub_rn(xt.z, V->centroid[2]);
-          const float dist = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
-          if (!(dist < G.r2)) continue;  // FLANN radius search: strict
+          if (!LISTED) {
+            const float ddx = __fsub_rn(xt.x, V->centroid[0]), ddy = __fsub_rn(xt.y, V->centroid[1]),
+                        ddz = __fsub_rn(xt.z, V->centroid[2]);
+            const float dist = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
+            if (!(dist < G.r2)) continue;  // FLANN radius search: strict
+          }
           const double xr[3] = {(double)xt.x - V->mean[0], (double)xt.y - V->mean[1], (double)xt.z - V->mean[2]};
           double C[9];
 #pragma unroll
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(NT) k_ndt_eval(const float4* __restrict__ src,
 
   int n_pairs_unused = 0;
   for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT)
-    ndt_point_eval(src[(size_t)seg * stride + i], E, G, tseg, wantH, d1, d2, acc, n_pairs_unused);
+    ndt_point_eval<false>(src[(size_t)seg * stride + i], E, G, tseg, wantH, d1, d2, acc, n_pairs_unused);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NACC; ++k) {
@@ -922,108 +926,198 @@ __global__ void __launch_bounds__(32) k_ndt_control(NdtState* __restrict__ st, N
 
 
 // ------------------------------------------------------------------------------------------------ persistent align
-// One thread-block cluster per (source, target) pair runs the WHOLE align -- every derivative evaluation of the Newton
-// iterations and of the More-Thuente line search, the 28-sum reduction, the Newton solve and the line-search state
-// machine -- inside a single launch: no launch per evaluation, no host polling (the per-evaluation path costs ~35 us of
-// launch + control per evaluation for ~10 us of arithmetic on a 6 k-point pair).  Every CTA owns an interleaved share of
-// the source points; the partial sums are pushed into every sibling's shared memory (st.async + mbarrier, as in
-// icp_persist.cuh) and every CTA redundantly runs the identical controller, so no broadcast is needed.
+// The WHOLE align of a few pairs -- every derivative evaluation of the Newton iterations and of the More-Thuente line
+// search, the 28-sum reduction, the Newton solve and the line-search state machine -- inside ONE cooperative launch that
+// spans the chip: no launch per evaluation, no host polling (the per-evaluation path costs ~35 us of launch + control per
+// evaluation for ~10 us of arithmetic on a 6 k-point pair, and polls the host every few evaluations).
+//   * the CTAs of the grid are divided evenly among the pairs; a pair's CTAs share its source points round-robin;
+//   * one evaluation = candidate pass (27 hash probes per point; hits compacted IN POINT ORDER into a shared-memory pair
+//     list) -> derivative bodies spread evenly over the threads (fixed pair -> thread map: reproducible fp64 sums) -> CTA
+//     partials to global memory -> ONE grid barrier -> every CTA of the pair sums the partials in CTA order and runs the
+//     identical controller on its own copy of the state, so nothing is broadcast.  The partial buffers alternate by
+//     evaluation parity (a CTA can be at most one evaluation ahead of another).
+// FP64-bound work with a long dependent chain per (point, voxel) pair: the latency of one evaluation is one body, which is
+// why the pairs get as many CTAs as the chip has rather than one cluster each.
 constexpr int NPT = 256;            // threads per CTA
-constexpr int NP_CLMAX = 8;
+constexpr int NP_CAP = 27 * NPT;    // (point, voxel) pairs of one round of NPT points
+
+// radiusSearch of one point over the 27 neighbouring voxels: bit c of the result = neighbour cell c holds a voxel whose
+// centroid is within the resolution of the transformed point (the test ndt_point_eval<false> applies)
+__device__ __forceinline__ unsigned ndt_candidates(const float4 p, const NdtEval& E, const NdtGridDev& G, int tseg) {
+  if (!finite3(p.x, p.y, p.z)) return 0u;
+  const float3 xt = xform_point(E.T, p.x, p.y, p.z);
+  if (!finite3(xt.x, xt.y, xt.z)) return 0u;
+  const int cx = floor_to_int_x86(fmul(xt.x, G.inv_leaf)), cy = floor_to_int_x86(fmul(xt.y, G.inv_leaf)),
+            cz = floor_to_int_x86(fmul(xt.z, G.inv_leaf));
+  if (!grid_in_range(cx, cy, cz)) return 0u;
+  unsigned mask = 0u;
+  int c = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx, ++c) {
+        const int vi = ndt_lookup(G, ndt_key(tseg, cx + dx, cy + dy, cz + dz));
+        if (vi < 0) continue;
+        const VoxRec* V = &G.vox[vi];
+        const float ddx = __fsub_rn(xt.x, V->centroid[0]), ddy = __fsub_rn(xt.y, V->centroid[1]),
+                    ddz = __fsub_rn(xt.z, V->centroid[2]);
+        const float dist = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
+        if (!(dist < G.r2)) continue;  // FLANN radius search: strict
+        mask |= 1u << c;
+      }
+  return mask;
+}
 
 struct NdtPersistSmem {
   NdtEval E;
   NdtState S;
+  int pl_vi[NP_CAP];                 // pair list of the current round: voxel ...
+  unsigned char pl_pt[NP_CAP];       // ... and the round-local index of its source point
+  int wtot[NPT / 32];
   double red[NPT / 32][NACC];
-  double xch[2][NP_CLMAX][NACC];
   double sums[NACC];
-  unsigned long long mbar[2];
   int finished;
 };
 
 __global__ void __launch_bounds__(NPT, 1)
 k_ndt_persist(const float4* __restrict__ src, const int* __restrict__ count, int stride, NdtState* __restrict__ st,
-              NdtEval* __restrict__ ev, NdtGridDev G, double d1, double d2, NdtCtl ctl, int max_evals,
+              NdtEval* __restrict__ ev, NdtGridDev G, double d1, double d2, NdtCtl ctl, int max_evals, int n_seg, int cpp /* CTAs per pair */,
+              double* __restrict__ gpart /* [2][n_seg][cpp][NACC] */, int* __restrict__ fin_eval /* [n_seg], preset to INT_MAX */,
               unsigned long long* __restrict__ work_count /* [0] (point, voxel) pairs of gradient evaluations, [1] of Hessian ones */) {
   __shared__ NdtPersistSmem M;
+  cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int CL = (int)cg::this_cluster().num_blocks();
-  const int crank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
-  const int seg = blockIdx.x / CL;
+  const int seg = blockIdx.x / cpp, crank = blockIdx.x % cpp;  // (gridDim.x == n_seg * cpp)
   static_assert(sizeof(NdtState) % 4 == 0 && sizeof(NdtEval) % 4 == 0, "copied as 32-bit words");
   for (int k = tid; k < (int)(sizeof(NdtEval) / 4); k += NPT) ((unsigned*)&M.E)[k] = ((const unsigned*)&ev[seg])[k];
   for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += NPT) ((unsigned*)&M.S)[k] = ((const unsigned*)&st[seg])[k];
-  if (tid == 0) {
-    mbar_init(smem_u32(&M.mbar[0]), 1);
-    mbar_init(smem_u32(&M.mbar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    M.finished = 0;
-  }
+  if (tid == 0) M.finished = 0;
   __syncthreads();
-  if (CL > 1) cg::this_cluster().sync();  // every CTA is running and has its barriers before anyone stores into it
   const int n = count[seg];
   const int tseg = G.shared_target ? 0 : seg;
   const float4* P = src + (size_t)seg * stride;
-  int parity = 0;
-  unsigned mphase = 0;
+  bool done = false;  // this pair has finished; its CTAs keep attending the grid barrier until every pair has
   unsigned long long pairs_g = 0, pairs_h = 0;
   for (int evals = 0; evals < max_evals; ++evals) {
-    const bool wantH = M.E.want_hessian != 0;
-    double acc[NACC];
+    double* part = gpart + (((size_t)(evals & 1) * n_seg + seg) * cpp) * NACC;
+    if (!done) {
+      const bool wantH = M.E.want_hessian != 0;
+      double acc[NACC];
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    int np = 0;
-    for (int i = tid * CL + crank; i < n; i += NPT * CL) ndt_point_eval(P[i], M.E, G, tseg, wantH, d1, d2, acc, np);
-    if (wantH) pairs_h += np; else pairs_g += np;
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      int np = 0;
+      // Rounds of NPT points per CTA (one per thread).  Pass 1 finds every point's voxels (27 hash probes: cheap, but
+      // different lanes hit different cells, so running the ~500-operation derivative body inside that loop would execute
+      // it up to 27 times per warp); pass 2 spreads the pairs evenly over the threads.  Pair j always goes to thread
+      // j % NPT: the fp64 sums keep a fixed order.
+      for (int base = crank; base < n; base += NPT * cpp) {
+        const int i = base + tid * cpp;
+        const float4 p = i < n ? P[i] : make_float4(NAN, NAN, NAN, 0.f);
+        const unsigned mask = ndt_candidates(p, M.E, G, tseg);
+        const int mycnt = __popc(mask);
+        int incl = mycnt;
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) {
-      const double v = warp_sum(acc[k]);
-      if (lane == 0) M.red[wid][k] = v;
-    }
-    __syncthreads();
-    const int buf = parity;
-    parity ^= 1;
-    if (wid == 0) {
-      double v = 0;
-      if (lane < NACC) {
-#pragma unroll
-        for (int w = 0; w < NPT / 32; ++w) v += M.red[w][lane];
-      }
-      if (CL > 1) {
-        const unsigned mb = smem_u32(&M.mbar[buf]);
-        if (lane < NACC) {
-          const unsigned slot_addr = smem_u32(&M.xch[buf][crank][lane]);
-          for (int rk = 0; rk < CL; ++rk) st_async_f64(mapa_u32(slot_addr, rk), v, mapa_u32(mb, rk));
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
         }
-        if (lane == 0) mbar_arrive_expect_tx(mb, (unsigned)(CL * NACC * sizeof(double)));
-        mbar_wait_cluster(mb, (mphase >> buf) & 1u);
-        if (lane < NACC) {
-          v = 0;
-          for (int rk = 0; rk < CL; ++rk) v += M.xch[buf][rk][lane];  // fixed rank order: identical on every CTA
+        if (lane == 31) M.wtot[wid] = incl;
+        __syncthreads();
+        int woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NPT / 32; ++w) {
+          const int c = M.wtot[w];
+          woff += (w < wid) ? c : 0;
+          total += c;
+        }
+        if (mask) {  // second, identical probe sequence: the voxel indices go straight into the list
+          int pos = woff + incl - mycnt;
+          const float3 xt = xform_point(M.E.T, p.x, p.y, p.z);
+          const int cx = floor_to_int_x86(fmul(xt.x, G.inv_leaf)), cy = floor_to_int_x86(fmul(xt.y, G.inv_leaf)),
+                    cz = floor_to_int_x86(fmul(xt.z, G.inv_leaf));
+          int c = 0;
+          for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+              for (int dx = -1; dx <= 1; ++dx, ++c)
+                if (mask & (1u << c)) {
+                  M.pl_vi[pos] = ndt_lookup(G, ndt_key(tseg, cx + dx, cy + dy, cz + dz));
+                  M.pl_pt[pos] = (unsigned char)tid;
+                  ++pos;
+                }
+        }
+        __syncthreads();
+        for (int j = tid; j < total; j += NPT) {
+          const int ii = base + (int)M.pl_pt[j] * cpp;
+          ndt_point_eval<true>(P[ii], M.E, G, tseg, wantH, d1, d2, acc, np, M.pl_vi[j]);
+        }
+        __syncthreads();  // the list is rewritten by the next round
+      }
+      if (wantH) pairs_h += np; else pairs_g += np;
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) M.red[wid][k] = v;
+      }
+      __syncthreads();
+      if (tid < NACC) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < NPT / 32; ++w) v += M.red[w][tid];
+        part[(size_t)crank * NACC + tid] = v;
+      }
+      __threadfence();
+    }
+    grid.sync();
+    {
+      bool all = true;
+      for (int sg = 0; sg < n_seg; ++sg) all = all && (__ldcg(&fin_eval[sg]) < evals);
+      if (all) break;  // (identical on every thread of the grid)
+    }
+    if (!done) {
+      {  // the pair's CTA partials, summed by 8 groups of lanes in a fixed order (identical on every CTA)
+        const int k = tid & 31, grp = tid >> 5;
+        double v = 0;
+        if (k < NACC)
+          for (int c = grp; c < cpp; c += NPT / 32) v += __ldcg(&part[(size_t)c * NACC + k]);
+        __syncthreads();  // (M.red was last read before the grid barrier)
+        if (k < NACC) M.red[grp][k] = v;
+        __syncthreads();
+        if (tid < NACC) {
+          double t = 0;
+#pragma unroll
+          for (int w = 0; w < NPT / 32; ++w) t += M.red[w][tid];
+          M.sums[tid] = t;
         }
       }
-      if (lane < NACC) M.sums[lane] = v;
-      __syncwarp();
-      if (lane == 0) M.finished = ndt_control_step(&M.S, &M.E, M.sums, ctl) ? 1 : 0;
+      __syncthreads();
+      if (tid == 0) M.finished = ndt_control_step(&M.S, &M.E, M.sums, ctl) ? 1 : 0;
+      __syncthreads();
+      if (M.finished) {
+        done = true;
+        if (crank == 0) {
+          for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += NPT) ((unsigned*)&st[seg])[k] = ((const unsigned*)&M.S)[k];
+          for (int k = tid; k < (int)(sizeof(NdtEval) / 4); k += NPT) ((unsigned*)&ev[seg])[k] = ((const unsigned*)&M.E)[k];
+          if (tid == 0) {
+            __threadfence();
+            fin_eval[seg] = evals;
+          }
+        }
+      }
     }
-    mphase ^= 1u << buf;
-    __syncthreads();
-    if (M.finished) break;
+    // Termination: a pair's first CTA records the evaluation at which the pair finished; everybody reads the records after
+    // the NEXT barrier and only trusts entries <= the previous evaluation, which are complete by then -- every CTA takes
+    // the same decision and leaves at the same barrier (one barrier per evaluation, one extra at the end).
   }
-  if (CL > 1) cg::this_cluster().sync();  // nobody leaves while a sibling may still store into its shared memory
-  if (crank == 0) {
+  if (!done && crank == 0) {  // evaluation budget exhausted: hand the state back as it stands
     for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += NPT) ((unsigned*)&st[seg])[k] = ((const unsigned*)&M.S)[k];
     for (int k = tid; k < (int)(sizeof(NdtEval) / 4); k += NPT) ((unsigned*)&ev[seg])[k] = ((const unsigned*)&M.E)[k];
   }
-  if (work_count) {
-    for (int o = 16; o > 0; o >>= 1) {
-      pairs_g += __shfl_down_sync(0xffffffffu, pairs_g, o);
-      pairs_h += __shfl_down_sync(0xffffffffu, pairs_h, o);
-    }
-    if (lane == 0) {
-      atomicAdd(&work_count[0], pairs_g);
-      atomicAdd(&work_count[1], pairs_h);
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    pairs_g += __shfl_down_sync(0xffffffffu, pairs_g, o);
+    pairs_h += __shfl_down_sync(0xffffffffu, pairs_h, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&work_count[0], pairs_g);
+    atomicAdd(&work_count[1], pairs_h);
   }
 }
 
@@ -1232,42 +1326,47 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   int chunk = 4, active = S;
   dim3 ge(nblk, S);
   const char* penv = getenv("RSPCL_NDT_PERSIST");
-  if (!sharded && !(penv && penv[0] == '0')) {
-    // whole align in one launch: one cluster per pair, as many CTAs per pair as one wave of the chip allows
-    int cl = ctx->sm_count / (S > 0 ? S : 1);
-    cl = cl < 1 ? 1 : (cl > NP_CLMAX ? NP_CLMAX : cl);
-    while (cl > 1 && src->max_count_hint / cl < NPT / 2) --cl;  // tiny clouds: more CTAs only add exchange latency
-    unsigned long long* d_work = nullptr;
-    CU(ctx, scratch_alloc(ctx, &d_work, 2));
-    CU(ctx, cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(cl * S));
-    cfg.blockDim = dim3(NPT);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)cl;
-    at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    unsigned long long hw[2] = {0, 0};
-    {
-      ProfScope prof(ctx, "k_ndt_persist", 0.0);
-      CU(ctx, cudaLaunchKernelEx(&cfg, k_ndt_persist, (const float4*)src->pts, (const int*)src->count, src->stride, st, ev, G, d1, d2, ctl,
-                                 (int)max_evals, d_work));
-      LAUNCH_CHECK(ctx);
-      prof.end();
-      if (ctx->prof_on) {
-        CU(ctx, small_d2h(ctx, hw, d_work, sizeof(hw)));
-        CU(ctx, ctx_sync(ctx));
-        // FP64 operations: per (point, voxel) pair ~135 for a gradient evaluation, ~456 with the Hessian (counted from
-        // ndt_point_eval); reported as "equivalent gradient pairs" so that one number carries both
-        prof.set_units((double)hw[0] + (double)hw[1] * (456.0 / 135.0));
+  // a few pairs: the whole align in ONE cooperative launch that spans the chip (k_ndt_persist); batches of many pairs keep
+  // the per-evaluation launches below, which fill the chip with two CTAs per SM and amortise their launches over the batch
+  if (!sharded && !(penv && penv[0] == '0') && S * 8 <= ctx->sm_count) {
+    int per_sm = 0;
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ndt_persist, NPT, 0));
+    int cpp = per_sm > 0 ? (ctx->sm_count * per_sm) / S : 0;
+    const int want = div_up(src->max_count_hint > 0 ? src->max_count_hint : 1, 32);  // >= 32 points per CTA
+    if (cpp > want) cpp = want;
+    if (cpp >= 1) {
+      unsigned long long* d_work = nullptr;
+      double* d_gpart = nullptr;
+      int* d_fin = nullptr;
+      CU(ctx, scratch_alloc(ctx, &d_work, 2));
+      CU(ctx, scratch_alloc(ctx, &d_gpart, (size_t)2 * S * cpp * NACC));
+      CU(ctx, scratch_alloc(ctx, &d_fin, (size_t)S));
+      CU(ctx, cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned long long), ctx->stream));
+      CU(ctx, cudaMemsetAsync(d_fin, 0x7F, (size_t)S * sizeof(int), ctx->stream));  // 0x7F7F7F7F: "not finished"
+      const float4* a_src = src->pts;
+      const int* a_cnt = src->count;
+      int a_stride = src->stride, a_max = (int)max_evals, a_S = S;
+      void* args[] = {(void*)&a_src, (void*)&a_cnt, (void*)&a_stride, (void*)&st, (void*)&ev, (void*)&G, (void*)&d1, (void*)&d2,
+                      (void*)&ctl, (void*)&a_max, (void*)&a_S, (void*)&cpp, (void*)&d_gpart, (void*)&d_fin, (void*)&d_work};
+      unsigned long long hw[2] = {0, 0};
+      {
+        ProfScope prof(ctx, "k_ndt_persist", 0.0);
+        CU(ctx, cudaLaunchCooperativeKernel((const void*)k_ndt_persist, dim3((unsigned)(S * cpp)), dim3(NPT), args, 0, ctx->stream));
+        LAUNCH_CHECK(ctx);
+        prof.end();
+        if (ctx->prof_on) {
+          CU(ctx, small_d2h(ctx, hw, d_work, sizeof(hw)));
+          CU(ctx, ctx_sync(ctx));
+          // FP64 operations: per (point, voxel) pair ~135 for a gradient evaluation, ~456 with the Hessian (counted from
+          // ndt_point_eval); reported as "equivalent gradient pairs" so that one number carries both
+          prof.set_units((double)hw[0] + (double)hw[1] * (456.0 / 135.0));
+        }
       }
+      scratch_free(ctx, d_work);
+      scratch_free(ctx, d_gpart);
+      scratch_free(ctx, d_fin);
+      active = 0;
     }
-    scratch_free(ctx, d_work);
-    active = 0;
   }
   while (active > 0 && done_evals < max_evals) {
     for (int k = 0; k < chunk; ++k) {

@@ -62,9 +62,9 @@ EXPORTS = [
     "rspcl_ctx_create", "rspcl_ctx_destroy", "rspcl_last_error", "rspcl_ctx_sync", "rspcl_timer_start",
     "rspcl_timer_stop", "rspcl_timer_mark", "rspcl_timer_span", "rspcl_launch_count", "rspcl_profile_enable", "rspcl_profile_reset", "rspcl_profile_get", "rspcl_host_alloc", "rspcl_host_free", "rspcl_cloud_create",
     "rspcl_cloud_destroy", "rspcl_cloud_n_seg", "rspcl_cloud_stride", "rspcl_cloud_dims", "rspcl_cloud_upload",
-    "rspcl_cloud_counts", "rspcl_cloud_download", "rspcl_cloud_invalidate_gray", "rspcl_cloud_download_xyz_pcl32", "rspcl_crop35", "rspcl_edge_extract", "rspcl_voxel_approx",
+    "rspcl_cloud_counts", "rspcl_cloud_download", "rspcl_cloud_invalidate_gray", "rspcl_cloud_download_xyz_pcl32", "rspcl_crop35", "rspcl_edge_extract", "rspcl_edge_labels", "rspcl_voxel_approx",
     "rspcl_voxel_keys", "rspcl_transform", "rspcl_concat", "rspcl_cloud_copy_segment", "rspcl_icp_reference_params",
-    "rspcl_icp_align", "rspcl_icp_align_dump", "rspcl_fitness", "rspcl_nearest", "rspcl_ndt_reference_params", "rspcl_ndt_align",
+    "rspcl_icp_align", "rspcl_icp_align_dump", "rspcl_debug_plan_clusters", "rspcl_fitness", "rspcl_nearest", "rspcl_ndt_reference_params", "rspcl_ndt_align",
     "rspcl_ndt_voxels", "rspcl_ndt_derivatives", "rspcl_register_pairs", "rspcl_register_sequence", "rspcl_comm_unique_id", "rspcl_comm_init",
     "rspcl_comm_destroy", "rspcl_icp_align_sharded", "rspcl_ndt_align_sharded",
 ]
@@ -305,6 +305,15 @@ def edge_extract(ctx, frames, t_low=40.0, t_high=100.0, want_mask=False, out_str
     mask = np.zeros((frames.n_seg, h, w), np.uint8) if want_mask else None
     ctx.check(lib().rspcl_edge_extract(ctx.h, frames.h, C.c_float(t_low), C.c_float(t_high), out.h, _p(mask)))
     return (out, mask) if want_mask else out
+
+
+def edge_labels(ctx, frames, th_depth_discon=0.2, max_search_neighbors=50, t_low=40.0, t_high=100.0):
+    """Per-pixel edge labels (1 NaN boundary, 2 occluding, 4 occluded, 16 RGB Canny): [n_seg, h, w] uint8."""
+    w, h = frames.dims()
+    lab = np.zeros((frames.n_seg, h, w), np.uint8)
+    ctx.check(lib().rspcl_edge_labels(ctx.h, frames.h, C.c_float(th_depth_discon), int(max_search_neighbors),
+                                      C.c_float(t_low), C.c_float(t_high), _p(lab)))
+    return lab
 
 
 def voxel_approx(ctx, cloud, leaf=(0.01, 0.01, 0.01), in_place=False):

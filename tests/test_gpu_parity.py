@@ -558,3 +558,26 @@ def test_register_sequence_matches_oracle_scheme(ctx, sweep3, scheme):
     for k, lo in ((2, 0), (1, len(v[2]))):
         exp = orc.transform(orc.transform(v[k], R.c_to_mat(res[k].T_coarse)), R.c_to_mat(res[k].T_fine))
         assert np.array_equal(t[lo:lo + len(v[k])].view(np.uint32), exp.view(np.uint32)), k
+
+
+def test_edge_labels_depth_classes_and_rgb(ctx, pair2):
+    """Row f2 (partial): the label image rs-pcl --edges shows -- NaN boundary / occluding / occluded from the depth channel
+    (OrganizedEdgeBase) plus the RGB-Canny bit -- bit-exact against the oracle, on a frame with NaN holes, (0,0,0) holes
+    and a depth step."""
+    fr, _ = pair2
+    rng = np.random.default_rng(61)
+    f = [fr[0].copy(), fr[1].copy()]
+    z = f[0]["z"].reshape(H, W)
+    z[100:160, 200:300] = np.nan                      # a NaN hole with finite pixels across it
+    z[300:340, 50:90] += 1.5                          # an occluded patch (farther than its surroundings)
+    z[5:8, :] = np.nan                                # NaNs reaching the image border: nothing to find across them
+    holes = rng.random(W * H) < 0.01
+    f[1]["z"][holes] = 0.0
+    frames = ctx.upload(f, W, H)
+    lab = R.edge_labels(ctx, frames)
+    for k in range(2):
+        exp = orc.depth_edge_labels(f[k], W, H)
+        m, _ = orc.canny(f[k], W, H)
+        exp = exp | np.where(m > 0, 16, 0).astype(np.uint8)
+        assert np.array_equal(lab[k], exp), (k, int((lab[k] != exp).sum()))
+    assert (lab[0] & 1).sum() > 0 and (lab[0] & 2).sum() > 0 and (lab[0] & 4).sum() > 0 and (lab[0] & 16).sum() > 3000

@@ -537,3 +537,32 @@ def test_pcd_round_trip(tmp_path, pair2):
     gen_scene.write_pcd(path, fr[0], 640, 480)
     back, w, h = gen_scene.read_pcd(path)
     assert (w, h) == (640, 480) and np.array_equal(back, fr[0])
+
+
+def test_depth_edge_labels_hand_cases():
+    """OrganizedEdgeBase restatement (orc_depth_edge_labels) on cases small enough to label by hand: a raised patch is
+    OCCLUDED (farther) and its rim OCCLUDING, a NaN hole with valid depth across it leaves no label when the depths agree,
+    NaNs that run into the image border make their finite neighbours NAN_BOUNDARY."""
+    W_, H_ = 12, 9
+    p = np.zeros(W_ * H_, orc.POINT)
+    p["z"] = 1.0
+    z = p["z"].reshape(H_, W_)
+    z[5:7, 8:10] = 2.0
+    z[3, 5] = np.nan
+    lab = orc.depth_edge_labels(p, W_, H_)
+    assert (lab[5:7, 8:10] == 4).all()                        # farther than its neighbours: occluded
+    assert lab[4, 7] == 2 and lab[7, 10] == 2 and lab[5, 7] == 2  # the rim in front of it: occluding
+    assert (lab[2:5, 4:7] == 0).all()                          # across the 1-pixel hole the depth is the same
+    assert (lab[0] == 0).all() and (lab[:, 0] == 0).all()      # border pixels are never labelled
+    q = p.copy()
+    q["z"].reshape(H_, W_)[:, :3] = np.nan                     # a NaN band touching the left border
+    lab = orc.depth_edge_labels(q, W_, H_)
+    assert (lab[1:-1, 3] == 1).all()                           # nothing finite across it: NaN boundary
+    # threshold is relative to the depth (edge_extractor.hpp:19 passes 0.2): a 15 % step is not an edge, a 25 % step is
+    s = np.zeros(W_ * H_, orc.POINT)
+    s["z"] = 2.0
+    s["z"].reshape(H_, W_)[:, 6:] = 2.3
+    assert (orc.depth_edge_labels(s, W_, H_) == 0).all()
+    s["z"].reshape(H_, W_)[:, 6:] = 2.6
+    lab = orc.depth_edge_labels(s, W_, H_)
+    assert (lab[1:-1, 5] == 2).all() and (lab[1:-1, 6] == 4).all()
