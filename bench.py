@@ -178,6 +178,23 @@ def cpu_sweep_pairs(frames, n_pairs, iters, coarse, threads):
     return time.perf_counter() - t0, Ts
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """File-descriptor level: native libraries (NCCL's version banner) must not write into the one-JSON-line stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -416,14 +433,8 @@ def point_sharded_leg(ctx, R, gen_scene, torch, dist, rank, world, dev, a, hbm_p
         uid = torch.from_numpy(R.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
         dist.broadcast(uid, 0)
         # (NCCL prints its version banner to stdout when the library creates its communicator: keep stdout = the JSON line)
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
+        with stdout_to_stderr():
             R.comm_init(ctx, world, rank, uid.cpu().numpy())
-        finally:
-            os.dup2(saved, 1)
-            os.close(saved)
     tgt = gen_scene.sample_room_surface(a.seed + 77, P)
     Tm = np.eye(4)
     Tm[:3, :3] = gen_scene.rot_axis([0.3, 1.0, 0.2], 0.0004)
@@ -538,7 +549,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
     numa = bind_to_gpu_numa_node(torch, dev)
     ctx = R.Context(dev)
