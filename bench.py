@@ -48,7 +48,7 @@ RADS = -0.523599  # icp_edge_based_registration.hpp:135
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 50; 10 for --impl reference, whose step is ~7 s of CPU)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=65, help="frames per GPU sweep (pairs = frames - 1); 65 = a 64-pair sweep (configs[3])")
@@ -68,7 +68,10 @@ def parse():
     ap.add_argument("--e2e-lock", default="nosync", choices=["sync", "nosync", "none"],
                     help="serialise transfers per direction (sync: hold the lock until the copy completed)")
     ap.add_argument("--e2e-trace", action="store_true", help="print per-chunk phase timestamps of the timed e2e pipeline to stderr")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 10 if a.impl == "reference" else 50
+    return a
 
 
 def forced_kw(iters):
