@@ -26,6 +26,13 @@ inline void jacobi_eigh(const S* A_in, S* w, S* V) {
         S apq = A[p * N + q];
         if (apq == S(0)) continue;
         S app = A[p * N + p], aqq = A[q * N + q];
+        // an off-diagonal entry that no longer registers against either diagonal entry is set to zero instead of being
+        // rotated (Rutishauser's test); without it rounding noise keeps `off` from ever reaching 0 and all 64 sweeps run
+        const S g = S(100) * std::fabs(apq);
+        if (std::fabs(app) + g == std::fabs(app) && std::fabs(aqq) + g == std::fabs(aqq)) {
+          A[p * N + q] = A[q * N + p] = S(0);
+          continue;
+        }
         S theta = (aqq - app) / (S(2) * apq);
         S t = (theta >= S(0) ? S(1) : S(-1)) / (std::fabs(theta) + std::sqrt(theta * theta + S(1)));
         S c = S(1) / std::sqrt(t * t + S(1));

@@ -96,6 +96,217 @@ __global__ void k_leaf_flags(const int* __restrict__ cell_start, const int* __re
     leaf_flag[c] = (c < nc && cell_start[c + 1] - cell_start[c] >= min_points) ? 1 : 0;
 }
 
+// ---- one-CTA voxel build for a single target of <= NB1_MAX points (configs[0] / configs[2] / the facade's per-frame aligns).
+// Replaces ~35 launches (keys, 8-bit radix passes over 64-bit keys, two scans, heads, starts, leaf flags) with ONE launch
+// that leaves the very same arrays behind for k_voxel_stats: sorted point indices, cell starts, leaf flags / ordinals,
+// and the 64-bit key at every cell head.  Keys are packed TIGHTLY inside the occupied cell box ((iz,iy,ix) major -> minor,
+// the order of ndt_key), so a 5 x 3 x 5 m scene at 1 m leaves sorts in 2-3 four-bit passes.  Stable LSD radix sort with a
+// contiguous chunk per thread: per-thread digit counts in shared memory, one block scan per pass, ordered scatter.
+constexpr int NB1_T = 1024;
+constexpr int NB1_MAX = 32 * NB1_T;   // <= 32 items per thread (keys / indices ping-pong in global memory, L1/L2-resident)
+constexpr int NB1_SMEM_MAX = 16384;   // up to here the sort runs entirely in shared memory (32-bit keys, 16-bit indices)
+
+struct Nb1Smem {
+  unsigned short hist[16][NB1_T];  // per-thread digit counts -> scatter bases (<= 32768 fits)
+  int wsum[32];
+  int box[6];
+  int tot;
+  int pad;
+};
+constexpr size_t NB1_SMEM_BYTES = sizeof(Nb1Smem) + (size_t)NB1_SMEM_MAX * 12;
+
+__device__ __forceinline__ int nb1_block_excl_scan(int v, Nb1Smem& S, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // wsum free
+  if (lane == 31) S.wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = S.wsum[lane], winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    S.wsum[lane] = winc - w;
+    if (lane == 31) S.tot = winc;
+  }
+  __syncthreads();
+  if (total) *total = S.tot;
+  return S.wsum[warp] + inc - v;
+}
+
+__device__ __forceinline__ int bits_for(int range) {  // bits to hold 0..range
+  return range <= 0 ? 0 : 32 - __clz(range);
+}
+
+// the phases after the keys exist; K / V = the key / index types of the storage the sort runs in
+template <typename K, typename V>
+__device__ __forceinline__ void nb1_sort_emit(K* ks, K* kd, V* vs, V* vd, Nb1Smem& S, int b0, int b1, int kbits, int n_valid,
+                                              int bx, int by, int mx, int my, int mz, int min_points,
+                                              unsigned long long* __restrict__ keys_out, int* __restrict__ vals_out,
+                                              int* __restrict__ cell_start, int* __restrict__ leaf_flag,
+                                              int* __restrict__ leaf_ord, int* __restrict__ n_cells_out,
+                                              int* __restrict__ n_leaves_out) {
+  const int t = threadIdx.x;
+  // ---- stable LSD radix sort, 4 bits per pass, over kbits + 1 bits (the extra bit sorts the invalid keys last)
+  for (int shift = 0; shift <= kbits; shift += 4) {
+#pragma unroll
+    for (int d = 0; d < 16; ++d) S.hist[d][t] = 0;
+    for (int i = b0; i < b1; ++i) S.hist[(unsigned)(ks[i] >> shift) & 15][t] += 1;  // column t is private to the thread
+    __syncthreads();
+    // exclusive scan of the (digit-major, thread-minor) counts: thread t owns 16 consecutive entries (two 128-bit words)
+    uint4* flat = reinterpret_cast<uint4*>(&S.hist[0][0]) + 2 * t;
+    uint4 q0 = flat[0], q1 = flat[1];
+    unsigned w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    int sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sum += (int)(w[q] & 0xFFFFu) + (int)(w[q] >> 16);
+    int run = nb1_block_excl_scan(sum, S, nullptr);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c0 = (int)(w[q] & 0xFFFFu), c1 = (int)(w[q] >> 16);
+      w[q] = (unsigned)run | ((unsigned)(run + c0) << 16);
+      run += c0 + c1;
+    }
+    flat[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    flat[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    __syncthreads();
+    for (int i = b0; i < b1; ++i) {
+      const K k = ks[i];
+      const unsigned pos = S.hist[(unsigned)(k >> shift) & 15][t]++;
+      kd[pos] = k;
+      vd[pos] = vs[i];
+    }
+    __syncthreads();
+    K* tk = ks; ks = kd; kd = tk;
+    V* tv = vs; vs = vd; vd = tv;
+  }
+  // ---- cell heads -> cell ids, cell starts, 64-bit keys at the heads, sorted point indices
+  int heads = 0;
+  for (int j = b0; j < b1; ++j) heads += (j < n_valid && (j == 0 || ks[j - 1] != ks[j])) ? 1 : 0;
+  int n_cells;
+  int cell = nb1_block_excl_scan(heads, S, &n_cells);
+  for (int j = b0; j < b1; ++j) {
+    vals_out[j] = (int)vs[j];
+    if (j < n_valid && (j == 0 || ks[j - 1] != ks[j])) {
+      const unsigned long long k = (unsigned long long)ks[j];
+      const int ix = (int)(k & ((1ull << bx) - 1)) + mx, iy = (int)((k >> bx) & ((1ull << by) - 1)) + my,
+                iz = (int)(k >> (bx + by)) + mz;
+      keys_out[j] = ndt_key(0, ix, iy, iz);
+      cell_start[cell++] = j;
+    }
+  }
+  if (t == 0) cell_start[n_cells] = n_valid, *n_cells_out = n_cells;
+  __syncthreads();
+  // ---- leaves: cells with >= min_points points, numbered in key order
+  const int Cc = (n_cells + NB1_T - 1) / NB1_T;
+  const int c0 = min(t * Cc, n_cells), c1 = min(c0 + Cc, n_cells);
+  int leaves = 0;
+  for (int c = c0; c < c1; ++c) {
+    const int f = (cell_start[c + 1] - cell_start[c] >= min_points) ? 1 : 0;
+    leaf_flag[c] = f;
+    leaves += f;
+  }
+  int n_leaves;
+  int ord = nb1_block_excl_scan(leaves, S, &n_leaves);
+  for (int c = c0; c < c1; ++c) {
+    leaf_ord[c] = ord;
+    ord += leaf_flag[c];
+  }
+  if (t == 0) *n_leaves_out = n_leaves;
+}
+
+__global__ void __launch_bounds__(NB1_T, 1)
+k_ndt_build_one(const float4* __restrict__ pts, const int* __restrict__ count, int N, float inv_leaf, int min_points,
+                unsigned long long* __restrict__ kA, unsigned long long* __restrict__ kB, int* __restrict__ vA,
+                int* __restrict__ vB, unsigned long long* __restrict__ keys_out, int* __restrict__ vals_out,
+                int* __restrict__ cell_start, int* __restrict__ leaf_flag, int* __restrict__ leaf_ord,
+                int* __restrict__ n_cells_out, int* __restrict__ n_leaves_out, int* __restrict__ range_flag) {
+  extern __shared__ __align__(16) unsigned char nb1_raw[];
+  Nb1Smem& S = *reinterpret_cast<Nb1Smem*>(nb1_raw);
+  const int t = threadIdx.x, lane = t & 31;
+  int n = count[0];
+  if (n > N) n = N;
+  // an odd chunk length keeps the chunked shared-memory walks (lane stride = C words) free of bank conflicts
+  const int C = ((N + NB1_T - 1) / NB1_T) | 1;
+  const int b0 = min(t * C, N), b1 = min(b0 + C, N);
+  // ---- occupied cell box
+  if (t < 3) S.box[t] = INT_MAX;
+  else if (t < 6) S.box[t] = INT_MIN;
+  __syncthreads();
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (int i = t; i < n; i += NB1_T) {  // coalesced walk
+    const float4 p = pts[i];
+    if (!finite3(p.x, p.y, p.z)) continue;
+    const int c[3] = {floor_to_int_x86(fmul(p.x, inv_leaf)), floor_to_int_x86(fmul(p.y, inv_leaf)),
+                      floor_to_int_x86(fmul(p.z, inv_leaf))};
+    if (!grid_in_range(c[0], c[1], c[2])) {
+      atomicExch(range_flag, 1);
+      continue;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) lo[a] = min(lo[a], c[a]), hi[a] = max(hi[a], c[a]);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if (lane == 0) atomicMin(&S.box[a], lo[a]), atomicMax(&S.box[3 + a], hi[a]);
+  }
+  __syncthreads();
+  const int mx = S.box[0], my = S.box[1], mz = S.box[2];
+  const bool any = S.box[3] >= mx;
+  const int bx = any ? bits_for(S.box[3] - mx) : 0, by = any ? bits_for(S.box[4] - my) : 0,
+            bz = any ? bits_for(S.box[5] - mz) : 0;
+  const int kbits = bx + by + bz;  // <= 48
+  const unsigned long long kinv = 1ull << kbits;
+  const bool in_smem = (N <= NB1_SMEM_MAX) && (kbits < 32);
+  unsigned* sk = reinterpret_cast<unsigned*>(nb1_raw + sizeof(Nb1Smem));  // [2][NB1_SMEM_MAX] keys
+  unsigned short* sv = reinterpret_cast<unsigned short*>(sk + 2 * NB1_SMEM_MAX);  // [2][NB1_SMEM_MAX] point indices
+  // ---- keys.  Coalesced walk over the points; item i lands in slot i of the (chunked) sort storage.
+  int nvalid_t = 0;
+  for (int i = t; i < N; i += NB1_T) {
+    unsigned long long k = kinv;
+    if (i < n) {
+      const float4 p = pts[i];
+      if (finite3(p.x, p.y, p.z)) {
+        const int ix = floor_to_int_x86(fmul(p.x, inv_leaf)), iy = floor_to_int_x86(fmul(p.y, inv_leaf)),
+                  iz = floor_to_int_x86(fmul(p.z, inv_leaf));
+        if (grid_in_range(ix, iy, iz)) {
+          k = ((unsigned long long)(unsigned)(iz - mz) << (bx + by)) | ((unsigned long long)(unsigned)(iy - my) << bx) |
+              (unsigned long long)(unsigned)(ix - mx);
+          ++nvalid_t;
+        }
+      }
+    }
+    if (in_smem) {
+      sk[i] = (unsigned)k;
+      sv[i] = (unsigned short)i;
+    } else {
+      kA[i] = k;
+      vA[i] = i;
+    }
+  }
+  int n_valid;
+  nb1_block_excl_scan(nvalid_t, S, &n_valid);
+  if (in_smem)
+    nb1_sort_emit<unsigned, unsigned short>(sk, sk + NB1_SMEM_MAX, sv, sv + NB1_SMEM_MAX, S, b0, b1, kbits, n_valid, bx, by, mx, my,
+                                            mz, min_points, keys_out, vals_out, cell_start, leaf_flag, leaf_ord, n_cells_out,
+                                            n_leaves_out);
+  else
+    nb1_sort_emit<unsigned long long, int>(kA, kB, vA, vB, S, b0, b1, kbits, n_valid, bx, by, mx, my, mz, min_points, keys_out,
+                                           vals_out, cell_start, leaf_flag, leaf_ord, n_cells_out, n_leaves_out);
+}
+
 // ---- symmetric 3x3 / 6x6 cyclic Jacobi (same rotation formulas as the oracle's stand-in for Eigen)
 template <int N>
 __device__ void jacobi_eigh(const double* A_in, double* w, double* V) {
@@ -113,6 +324,13 @@ __device__ void jacobi_eigh(const double* A_in, double* w, double* V) {
         const double apq = A[p * N + q];
         if (apq == 0.0) continue;
         const double app = A[p * N + p], aqq = A[q * N + q];
+        // negligible against both diagonal entries: zero it instead of rotating (same test as the oracle; without it
+        // rounding noise keeps `off` above 0 and all 64 sweeps run -- 0.37 ms of one thread per voxel)
+        const double g = __dmul_rn(100.0, fabs(apq));
+        if (__dadd_rn(fabs(app), g) == fabs(app) && __dadd_rn(fabs(aqq), g) == fabs(aqq)) {
+          A[p * N + q] = A[q * N + p] = 0.0;
+          continue;
+        }
         const double theta = __ddiv_rn(__dsub_rn(aqq, app), __dmul_rn(2.0, apq));
         const double t = __ddiv_rn(theta >= 0.0 ? 1.0 : -1.0,
                                    __dadd_rn(fabs(theta), __dsqrt_rn(__dadd_rn(__dmul_rn(theta, theta), 1.0))));
@@ -171,38 +389,68 @@ __device__ void inv3(const double* M, double* I) {
 }
 
 // One thread per accepted cell: sequential fp64 sums in input order, then the VoxelGridCovariance second pass.
-__global__ void k_voxel_stats(const float4* __restrict__ pts, int stride, int pstride, const unsigned long long* __restrict__ keys,
-                              const int* __restrict__ vals, const int* __restrict__ cell_start, const int* __restrict__ leaf_flag,
-                              const int* __restrict__ leaf_ord, const int* __restrict__ n_cells, double eig_mult,
-                              VoxRec* __restrict__ vox, unsigned long long* __restrict__ hkeys, int* __restrict__ hvals,
-                              unsigned cap_mask, int* __restrict__ nvox_seg) {
+// One WARP per cell.  The per-voxel sums are sequential in point order (VoxelGridCovariance accumulates mean_ and cov_
+// point by point in double; the oracle does the same), so the order of every accumulator's additions is fixed -- but the
+// 3 + 9 double accumulators and the 3 float centroid sums are independent chains.  The warp loads 32 points at a time
+// (coalesced indices, gathered points), every lane forms the 12 addends of ITS point (the products are order-free) and
+// parks them in shared memory; lanes 0..11 then run one dependent DADD chain each over the 32 rows, lanes 12..14 the float
+// chains.  A cell of 2000 points costs 2000 chained DADDs, not 2000 chained global-memory round trips.
+constexpr int VS_WARPS = 8, VS_PAD = 17;
+__global__ void __launch_bounds__(VS_WARPS * 32)
+k_voxel_stats(const float4* __restrict__ pts, int stride, int pstride, const unsigned long long* __restrict__ keys,
+              const int* __restrict__ vals, const int* __restrict__ cell_start, const int* __restrict__ leaf_flag,
+              const int* __restrict__ leaf_ord, const int* __restrict__ n_cells, double eig_mult,
+              VoxRec* __restrict__ vox, unsigned long long* __restrict__ hkeys, int* __restrict__ hvals,
+              unsigned cap_mask, int* __restrict__ nvox_seg) {
+  __shared__ double s_add[VS_WARPS][32][VS_PAD];  // [point][addend], padded: conflict-free 64-bit rows and columns
+  __shared__ float s_xyz[VS_WARPS][32][3];
   const int nc = *n_cells;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int c = blockIdx.x * VS_WARPS + wib; c < nc; c += gridDim.x * VS_WARPS) {
     if (!leaf_flag[c]) continue;
     const int b = cell_start[c], e = cell_start[c + 1], n = e - b;
     const unsigned long long key = keys[b];
     const int seg = (int)(key >> 48);
+    double acc = 0.0;
+    float csf = 0.f;
+    for (int base = b; base < e; base += 32) {
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the end add +0 (exact)
+      if (base + lane < e) p = pts[(size_t)seg * stride + vals[base + lane]];
+      const double v[3] = {(double)p.x, (double)p.y, (double)p.z};
+      __syncwarp();
+      double* row = s_add[wib][lane];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        row[a] = v[a];
+        s_xyz[wib][lane][a] = a == 0 ? p.x : (a == 1 ? p.y : p.z);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) row[3 + a * 3 + q] = __dmul_rn(v[a], v[q]);
+      }
+      __syncwarp();
+      if (lane < 12) {
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) acc = __dadd_rn(acc, s_add[wib][q][lane]);
+      } else if (lane < 15) {
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) csf = fadd(csf, s_xyz[wib][q][lane - 12]);
+      }
+    }
+    double sum[3], sxx[9];
+    float cs[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      sum[a] = __shfl_sync(0xffffffffu, acc, a);
+      cs[a] = __shfl_sync(0xffffffffu, csf, 12 + a);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sxx[k] = __shfl_sync(0xffffffffu, acc, 3 + k);
+    if (lane != 0) continue;
     VoxRec R;
     R.ijk[0] = (int)(key & 0xFFFF) - 32768;
     R.ijk[1] = (int)((key >> 16) & 0xFFFF) - 32768;
     R.ijk[2] = (int)((key >> 32) & 0xFFFF) - 32768;
     R.npts = n;
     R.pad = 0;
-    double sum[3] = {0, 0, 0}, sxx[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    float cs[3] = {0.f, 0.f, 0.f};
-    for (int j = b; j < e; ++j) {
-      const float4 p = pts[(size_t)seg * stride + vals[j]];
-      const double v[3] = {(double)p.x, (double)p.y, (double)p.z};
-      cs[0] = fadd(cs[0], p.x);
-      cs[1] = fadd(cs[1], p.y);
-      cs[2] = fadd(cs[2], p.z);
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        sum[a] = __dadd_rn(sum[a], v[a]);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) sxx[a * 3 + q] = __dadd_rn(sxx[a * 3 + q], __dmul_rn(v[a], v[q]));
-      }
-    }
     const double dn = (double)n;
     for (int a = 0; a < 3; ++a) {
       R.centroid[a] = __fdiv_rn(cs[a], (float)n);
@@ -1197,6 +1445,8 @@ int ndt_grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, const rspcl_ndt_param
   CU(ctx, scratch_alloc(ctx, &tkeys, (size_t)N));
   CU(ctx, scratch_alloc(ctx, &vals, (size_t)N));
   CU(ctx, scratch_alloc(ctx, &tvals, (size_t)N));
+  unsigned long long* flags_keys = nullptr;  // the one-CTA build's 64-bit keys at the cell heads
+  CU(ctx, scratch_alloc(ctx, &flags_keys, (size_t)N));
   CU(ctx, scratch_alloc(ctx, &flags, (size_t)N));
   CU(ctx, scratch_alloc(ctx, &ord, (size_t)N));
   CU(ctx, scratch_alloc(ctx, &cell_start, (size_t)N + 1));
@@ -1204,25 +1454,41 @@ int ndt_grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, const rspcl_ndt_param
   CU(ctx, scratch_alloc(ctx, &leaf_ord, (size_t)N));
   CU(ctx, scratch_alloc(ctx, &n_cells, 1));
   CU(ctx, scratch_alloc(ctx, &n_valid, 1));
-  CU(ctx, cudaMemsetAsync(n_valid, 0, sizeof(int), ctx->stream));
-  dim3 gk(blocks_per_seg(ctx, S, pstride, 256), S);
-  k_ndt_keys<<<gk, 256, 0, ctx->stream>>>(tgt->pts, tgt->count, tgt->stride, pstride, G->inv_leaf, keys, vals, d_range);
-  LAUNCH_CHECK(ctx);
-  int rc = radix_sort_pairs(ctx, keys, vals, tkeys, tvals, N);
-  if (rc) return rc;
+  CU(ctx, scratch_alloc(ctx, &G->n_leaves, 1));
   int nb = div_up(N, 256);
   if (nb > 16 * ctx->sm_count) nb = 16 * ctx->sm_count;
-  k_cell_heads<<<nb, 256, 0, ctx->stream>>>(keys, N, flags, n_valid);
-  LAUNCH_CHECK(ctx);
-  rc = rspcl_exclusive_scan_i32(ctx, flags, ord, N, n_cells);
-  if (rc) return rc;
-  k_cell_starts<<<nb, 256, 0, ctx->stream>>>(flags, ord, N, n_cells, n_valid, cell_start);
-  LAUNCH_CHECK(ctx);
-  k_leaf_flags<<<nb, 256, 0, ctx->stream>>>(cell_start, n_cells, prm->min_points_per_voxel, leaf_flag, N);
-  LAUNCH_CHECK(ctx);
-  CU(ctx, scratch_alloc(ctx, &G->n_leaves, 1));
-  rc = rspcl_exclusive_scan_i32(ctx, leaf_flag, leaf_ord, N, G->n_leaves);
-  if (rc) return rc;
+  int rc = RSPCL_OK;
+  const char* benv = getenv("RSPCL_NDT_BUILD_ONE");
+  unsigned long long* head_keys = keys;  // where k_voxel_stats finds the key of a cell's first point
+  int* sorted_vals = vals;
+  if (S == 1 && N <= NB1_MAX && !(benv && benv[0] == '0')) {
+    // one target of a few ten thousand points: the whole build up to the voxel statistics in ONE launch
+    CU(ctx, cudaFuncSetAttribute(k_ndt_build_one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NB1_SMEM_BYTES));
+    k_ndt_build_one<<<1, NB1_T, NB1_SMEM_BYTES, ctx->stream>>>(tgt->pts, tgt->count, (int)N, G->inv_leaf,
+                                                                prm->min_points_per_voxel, keys, tkeys, vals, tvals,
+                                                                reinterpret_cast<unsigned long long*>(flags_keys), ord,
+                                                                cell_start, leaf_flag, leaf_ord, n_cells, G->n_leaves, d_range);
+    LAUNCH_CHECK(ctx);
+    head_keys = reinterpret_cast<unsigned long long*>(flags_keys);
+    sorted_vals = ord;
+  } else {
+    CU(ctx, cudaMemsetAsync(n_valid, 0, sizeof(int), ctx->stream));
+    dim3 gk(blocks_per_seg(ctx, S, pstride, 256), S);
+    k_ndt_keys<<<gk, 256, 0, ctx->stream>>>(tgt->pts, tgt->count, tgt->stride, pstride, G->inv_leaf, keys, vals, d_range);
+    LAUNCH_CHECK(ctx);
+    rc = radix_sort_pairs(ctx, keys, vals, tkeys, tvals, N);
+    if (rc) return rc;
+    k_cell_heads<<<nb, 256, 0, ctx->stream>>>(keys, N, flags, n_valid);
+    LAUNCH_CHECK(ctx);
+    rc = rspcl_exclusive_scan_i32(ctx, flags, ord, N, n_cells);
+    if (rc) return rc;
+    k_cell_starts<<<nb, 256, 0, ctx->stream>>>(flags, ord, N, n_cells, n_valid, cell_start);
+    LAUNCH_CHECK(ctx);
+    k_leaf_flags<<<nb, 256, 0, ctx->stream>>>(cell_start, n_cells, prm->min_points_per_voxel, leaf_flag, N);
+    LAUNCH_CHECK(ctx);
+    rc = rspcl_exclusive_scan_i32(ctx, leaf_flag, leaf_ord, N, G->n_leaves);
+    if (rc) return rc;
+  }
   const int minp = prm->min_points_per_voxel > 0 ? prm->min_points_per_voxel : 1;
   G->vox_cap = N / minp + 1;
   unsigned cap = 1024;
@@ -1234,13 +1500,16 @@ int ndt_grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, const rspcl_ndt_param
   CU(ctx, scratch_alloc(ctx, &G->nvox_seg, (size_t)S));
   CU(ctx, cudaMemsetAsync(G->hkeys, 0xFF, (size_t)cap * sizeof(unsigned long long), ctx->stream));
   CU(ctx, cudaMemsetAsync(G->nvox_seg, 0, (size_t)S * sizeof(int), ctx->stream));
-  k_voxel_stats<<<nb, 128, 0, ctx->stream>>>(tgt->pts, tgt->stride, pstride, keys, vals, cell_start, leaf_flag, leaf_ord, n_cells,
+  int nbw = div_up(N, 8);  // one warp per cell, grid-stride over the cells
+  if (nbw > 8 * ctx->sm_count) nbw = 8 * ctx->sm_count;
+  k_voxel_stats<<<nbw, 256, 0, ctx->stream>>>(tgt->pts, tgt->stride, pstride, head_keys, sorted_vals, cell_start, leaf_flag, leaf_ord, n_cells,
                                              prm->min_covar_eigvalue_mult, G->vox, G->hkeys, G->hvals, G->cap_mask, G->nvox_seg);
   LAUNCH_CHECK(ctx);
   scratch_free(ctx, keys);
   scratch_free(ctx, tkeys);
   scratch_free(ctx, vals);
   scratch_free(ctx, tvals);
+  scratch_free(ctx, flags_keys);
   scratch_free(ctx, flags);
   scratch_free(ctx, ord);
   scratch_free(ctx, cell_start);
