@@ -1189,30 +1189,36 @@ __global__ void __launch_bounds__(32) k_ndt_control(NdtState* __restrict__ st, N
 constexpr int NPT = 256;            // threads per CTA
 constexpr int NP_CAP = 27 * NPT;    // (point, voxel) pairs of one round of NPT points
 
-// radiusSearch of one point over the 27 neighbouring voxels: bit c of the result = neighbour cell c holds a voxel whose
-// centroid is within the resolution of the transformed point (the test ndt_point_eval<false> applies)
-__device__ __forceinline__ unsigned ndt_candidates(const float4 p, const NdtEval& E, const NdtGridDev& G, int tseg) {
-  if (!finite3(p.x, p.y, p.z)) return 0u;
-  const float3 xt = xform_point(E.T, p.x, p.y, p.z);
-  if (!finite3(xt.x, xt.y, xt.z)) return 0u;
-  const int cx = floor_to_int_x86(fmul(xt.x, G.inv_leaf)), cy = floor_to_int_x86(fmul(xt.y, G.inv_leaf)),
-            cz = floor_to_int_x86(fmul(xt.z, G.inv_leaf));
-  if (!grid_in_range(cx, cy, cz)) return 0u;
-  unsigned mask = 0u;
-  int c = 0;
-  for (int dz = -1; dz <= 1; ++dz)
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx, ++c) {
-        const int vi = ndt_lookup(G, ndt_key(tseg, cx + dx, cy + dy, cz + dz));
-        if (vi < 0) continue;
-        const VoxRec* V = &G.vox[vi];
-        const float ddx = __fsub_rn(xt.x, V->centroid[0]), ddy = __fsub_rn(xt.y, V->centroid[1]),
-                    ddz = __fsub_rn(xt.z, V->centroid[2]);
-        const float dist = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
-        if (!(dist < G.r2)) continue;  // FLANN radius search: strict
-        mask |= 1u << c;
-      }
-  return mask;
+// radiusSearch of one point over the 27 neighbouring voxels (the test ndt_point_eval<false> applies), cell by cell:
+// one (point, neighbour cell) probe of that search: the voxel index, or -1
+struct NdtPointCell {
+  float3 xt;
+  int cx, cy, cz;
+  bool ok;
+};
+__device__ __forceinline__ NdtPointCell ndt_point_cell(const float4 p, const NdtEval& E, const NdtGridDev& G) {
+  NdtPointCell r;
+  r.ok = false;
+  r.xt = make_float3(0.f, 0.f, 0.f);
+  r.cx = r.cy = r.cz = 0;
+  if (!finite3(p.x, p.y, p.z)) return r;
+  r.xt = xform_point(E.T, p.x, p.y, p.z);
+  if (!finite3(r.xt.x, r.xt.y, r.xt.z)) return r;
+  r.cx = floor_to_int_x86(fmul(r.xt.x, G.inv_leaf));
+  r.cy = floor_to_int_x86(fmul(r.xt.y, G.inv_leaf));
+  r.cz = floor_to_int_x86(fmul(r.xt.z, G.inv_leaf));
+  r.ok = grid_in_range(r.cx, r.cy, r.cz);
+  return r;
+}
+__device__ __forceinline__ int ndt_probe(const NdtPointCell& pc, int c, const NdtGridDev& G, int tseg) {
+  const int dz = c / 9 - 1, dy = (c / 3) % 3 - 1, dx = c % 3 - 1;  // c = ((dz+1)*3 + (dy+1))*3 + (dx+1), as ndt_candidates
+  const int vi = ndt_lookup(G, ndt_key(tseg, pc.cx + dx, pc.cy + dy, pc.cz + dz));
+  if (vi < 0) return -1;
+  const VoxRec* V = &G.vox[vi];
+  const float ddx = __fsub_rn(pc.xt.x, __ldg(&V->centroid[0])), ddy = __fsub_rn(pc.xt.y, __ldg(&V->centroid[1])),
+              ddz = __fsub_rn(pc.xt.z, __ldg(&V->centroid[2]));
+  const float dist = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
+  return dist < G.r2 ? vi : -1;  // FLANN radius search: strict
 }
 
 struct NdtPersistSmem {
@@ -1253,14 +1259,31 @@ k_ndt_persist(const float4* __restrict__ src, const int* __restrict__ count, int
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
       int np = 0;
-      // Rounds of NPT points per CTA (one per thread).  Pass 1 finds every point's voxels (27 hash probes: cheap, but
-      // different lanes hit different cells, so running the ~500-operation derivative body inside that loop would execute
-      // it up to 27 times per warp); pass 2 spreads the pairs evenly over the threads.  Pair j always goes to thread
-      // j % NPT: the fp64 sums keep a fixed order.
+      // Rounds of NPT points per CTA.  Pass 1 finds every point's voxels: the 27 x (points of the round) hash probes are
+      // dealt out in contiguous chunks over ALL the threads -- a round of 40 points is 1080 probes, 5 per thread, not 27
+      // dependent probe chains on each of 40 threads -- and the hits are compacted, in (point, cell) order, into the pair
+      // list; pass 2 spreads the pairs evenly over the threads (running the ~500-operation derivative body inside the probe
+      // loop would execute it once per probe and warp).  Pair j always goes to thread j % NPT: the fp64 sums keep a fixed
+      // order.
       for (int base = crank; base < n; base += NPT * cpp) {
-        const int i = base + tid * cpp;
-        const float4 p = i < n ? P[i] : make_float4(NAN, NAN, NAN, 0.f);
-        const unsigned mask = ndt_candidates(p, M.E, G, tseg);
+        const int npl = min(NPT, (n - base + cpp - 1) / cpp);  // the round's points: i = base + pl * cpp, pl < npl
+        const int items = npl * 27;
+        const int C = (items + NPT - 1) / NPT;  // <= 27
+        const int j0 = min(tid * C, items), j1 = min(j0 + C, items);
+        unsigned mask = 0u;  // bit q: probe j0 + q found a voxel within the resolution
+        {
+          int pl_cur = -1;
+          NdtPointCell pc;
+          pc.ok = false;
+          for (int j = j0; j < j1; ++j) {
+            const int pl = j / 27;
+            if (pl != pl_cur) {
+              pl_cur = pl;
+              pc = ndt_point_cell(P[base + pl * cpp], M.E, G);
+            }
+            if (pc.ok && ndt_probe(pc, j - pl * 27, G, tseg) >= 0) mask |= 1u << (j - j0);
+          }
+        }
         const int mycnt = __popc(mask);
         int incl = mycnt;
 #pragma unroll
@@ -1277,20 +1300,22 @@ k_ndt_persist(const float4* __restrict__ src, const int* __restrict__ count, int
           woff += (w < wid) ? c : 0;
           total += c;
         }
-        if (mask) {  // second, identical probe sequence: the voxel indices go straight into the list
+        if (mask) {  // the hits again (cached lines), straight into the list
           int pos = woff + incl - mycnt;
-          const float3 xt = xform_point(M.E.T, p.x, p.y, p.z);
-          const int cx = floor_to_int_x86(fmul(xt.x, G.inv_leaf)), cy = floor_to_int_x86(fmul(xt.y, G.inv_leaf)),
-                    cz = floor_to_int_x86(fmul(xt.z, G.inv_leaf));
-          int c = 0;
-          for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-              for (int dx = -1; dx <= 1; ++dx, ++c)
-                if (mask & (1u << c)) {
-                  M.pl_vi[pos] = ndt_lookup(G, ndt_key(tseg, cx + dx, cy + dy, cz + dz));
-                  M.pl_pt[pos] = (unsigned char)tid;
-                  ++pos;
-                }
+          int pl_cur = -1;
+          NdtPointCell pc;
+          pc.ok = false;
+          for (int q = 0; q < j1 - j0; ++q) {
+            if (!(mask & (1u << q))) continue;
+            const int j = j0 + q, pl = j / 27;
+            if (pl != pl_cur) {
+              pl_cur = pl;
+              pc = ndt_point_cell(P[base + pl * cpp], M.E, G);
+            }
+            M.pl_vi[pos] = ndt_probe(pc, j - pl * 27, G, tseg);
+            M.pl_pt[pos] = (unsigned char)pl;
+            ++pos;
+          }
         }
         __syncthreads();
         for (int j = tid; j < total; j += NPT) {
