@@ -85,6 +85,74 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
+// steps 2 and 3 of k_canny_nms.  INTERIOR = the tile and its 3-pixel halo lie inside the image (three tiles in four at
+// 640x480): every clamp is the identity and every position is in the image, so the index arithmetic collapses.
+template <bool INTERIOR>
+__device__ __forceinline__ void canny_blur_sobel(float (*s_gray)[GW + 1], float (*s_blur)[BW + 1], float (*s_mag)[MW + 1],
+                                                 uint8_t (*s_dir)[TW], int tid, int r0, int c0, int w, int h, float t_low) {
+  // 2. blur evaluated AT THE CLAMPED COORDINATE of every halo-2 position (what the Sobel pass will read)
+  for (int k = tid; k < BH * BW; k += 256) {
+    int i = k / BW, j = k % BW;
+    int gi = i + 1, gj = j + 1;
+    if (!INTERIOR) {
+      int r = clampi(r0 - 2 + i, 0, h - 1), c = clampi(c0 - 2 + j, 0, w - 1);
+      gi = r - (r0 - 3), gj = c - (c0 - 3);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int kr = 0; kr < 3; ++kr)
+#pragma unroll
+      for (int kc = 0; kc < 3; ++kc) {
+        // in-image neighbour clamp is already baked into s_gray as long as (r,c) itself is in the image
+        acc = fadd(acc, fmul(c_gauss[kr * 3 + kc], s_gray[gi + kr - 1][gj + kc - 1]));
+      }
+    s_blur[i][j] = acc;
+  }
+  __syncthreads();
+  // 3. Sobel + magnitude on the halo-1 region (only in-image positions are ever consumed)
+  for (int k = tid; k < MH * MW; k += 256) {
+    int i = k / MW, j = k % MW;
+    int r = r0 - 1 + i, c = c0 - 1 + j;
+    float m = 0.f;
+    const bool centre = i >= 1 && i <= TH && j >= 1 && j <= TW;
+    if (INTERIOR || (r >= 0 && r < h && c >= 0 && c < w)) {
+      // blur(clamp(r+dr), clamp(c+dc)) lives at tile index (clamped coordinate - (origin-2))
+      int bi[3], bj[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        bi[d] = INTERIOR ? i + d : clampi(r + d - 1, 0, h - 1) - (r0 - 2);
+        bj[d] = INTERIOR ? j + d : clampi(c + d - 1, 0, w - 1) - (c0 - 2);
+      }
+      // Sobel X {-1,0,1,-2,0,2,-1,0,1} and Y {-1,-2,-1,0,0,0,1,2,1} as the 9-tap correlations PCL runs, taps in row-major
+      // order from a zero accumulator.  The zero taps add +-0 to a finite sum (the blurred image is finite) and the +-1 /
+      // +-2 products are exact, so they are written as the adds and doublings they amount to: same bits, a third of
+      // the operations.
+      const float v00 = s_blur[bi[0]][bj[0]], v01 = s_blur[bi[0]][bj[1]], v02 = s_blur[bi[0]][bj[2]];
+      const float v10 = s_blur[bi[1]][bj[0]], v12 = s_blur[bi[1]][bj[2]];
+      const float v20 = s_blur[bi[2]][bj[0]], v21 = s_blur[bi[2]][bj[1]], v22 = s_blur[bi[2]][bj[2]];
+      float gx = fadd(0.f, -v00);
+      gx = fadd(gx, v02);
+      gx = fadd(gx, -fadd(v10, v10));
+      gx = fadd(gx, fadd(v12, v12));
+      gx = fadd(gx, -v20);
+      gx = fadd(gx, v22);
+      float gy = fadd(0.f, -v00);
+      gy = fadd(gy, -fadd(v01, v01));
+      gy = fadd(gy, -v02);
+      gy = fadd(gy, v20);
+      gy = fadd(gy, fadd(v21, v21));
+      gy = fadd(gy, v22);
+      m = __fsqrt_rn(fadd(fmul(gx, gx), fmul(gy, gy)));
+      // the direction is only ever read for centre pixels that pass the low threshold (suppressNonMaxima)
+      if (centre) s_dir[i - 1][j - 1] = !(m < t_low) ? (uint8_t)direction_bin_fast(gy, gx) : (uint8_t)255;
+    } else if (centre) {
+      s_dir[i - 1][j - 1] = 255;
+    }
+    s_mag[i][j] = m;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ gray, int w, int h, int stride, float t_low,
                                                    float t_high, uint8_t* __restrict__ cls, int* __restrict__ parent) {
   __shared__ float s_gray[GH][GW + 1];
@@ -93,10 +161,13 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
   __shared__ uint8_t s_dir[TH][TW];  // direction bin of the centre pixels that can survive (magnitude >= t_low), else 255
   __shared__ uint8_t s_cls[TH][TW];
   __shared__ int s_par[TH * TW];  // tile-local union-find (parents are local pixel indices i * TW + j)
+  __shared__ unsigned short s_list[TH * TW];  // the tile's candidates (any order)
+  __shared__ int s_ncand;
   const int seg = blockIdx.z;
   const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const uint8_t* g = gray + (size_t)seg * stride;
+  if (tid == 0) s_ncand = 0;
 
   // 1. gray tile with replicate borders (Convolution BOUNDARY_OPTION_CLAMP).  Tiles whose halo lies inside the row (all
   //    but the first / last tile column) and whose rows are 16-byte aligned take 128-bit loads: the GW = 70 bytes of a
@@ -122,68 +193,21 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
     }
   }
   __syncthreads();
-  // 2. blur evaluated AT THE CLAMPED COORDINATE of every halo-2 position (what the Sobel pass will read)
-  for (int k = tid; k < BH * BW; k += 256) {
-    int i = k / BW, j = k % BW;
-    int r = clampi(r0 - 2 + i, 0, h - 1), c = clampi(c0 - 2 + j, 0, w - 1);
-    int gi = r - (r0 - 3), gj = c - (c0 - 3);
-    float acc = 0.f;
-#pragma unroll
-    for (int kr = 0; kr < 3; ++kr)
-#pragma unroll
-      for (int kc = 0; kc < 3; ++kc) {
-        // in-image neighbour clamp is already baked into s_gray as long as (r,c) itself is in the image
-        acc = fadd(acc, fmul(c_gauss[kr * 3 + kc], s_gray[gi + kr - 1][gj + kc - 1]));
-      }
-    s_blur[i][j] = acc;
-  }
-  __syncthreads();
-  // 3. Sobel + magnitude on the halo-1 region (only in-image positions are ever consumed)
-  for (int k = tid; k < MH * MW; k += 256) {
-    int i = k / MW, j = k % MW;
-    int r = r0 - 1 + i, c = c0 - 1 + j;
-    float m = 0.f;
-    if (r >= 0 && r < h && c >= 0 && c < w) {
-      // blur(clamp(r+dr), clamp(c+dc)) lives at tile index (clamped coordinate - (origin-2))
-      int bi[3], bj[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        bi[d] = clampi(r + d - 1, 0, h - 1) - (r0 - 2);
-        bj[d] = clampi(c + d - 1, 0, w - 1) - (c0 - 2);
-      }
-      // Sobel X {-1,0,1,-2,0,2,-1,0,1} and Y {-1,-2,-1,0,0,0,1,2,1} as the 9-tap correlations PCL runs, taps in row-major
-      // order from a zero accumulator.  The zero taps add +-0 to a finite sum (the blurred image is finite) and the +-1 /
-      // +-2 products are exact, so they are written as the adds and doublings they amount to: same bits, a third of
-      // the operations.
-      const float v00 = s_blur[bi[0]][bj[0]], v01 = s_blur[bi[0]][bj[1]], v02 = s_blur[bi[0]][bj[2]];
-      const float v10 = s_blur[bi[1]][bj[0]], v12 = s_blur[bi[1]][bj[2]];
-      const float v20 = s_blur[bi[2]][bj[0]], v21 = s_blur[bi[2]][bj[1]], v22 = s_blur[bi[2]][bj[2]];
-      float gx = fadd(0.f, -v00);
-      gx = fadd(gx, v02);
-      gx = fadd(gx, -fadd(v10, v10));
-      gx = fadd(gx, fadd(v12, v12));
-      gx = fadd(gx, -v20);
-      gx = fadd(gx, v22);
-      float gy = fadd(0.f, -v00);
-      gy = fadd(gy, -fadd(v01, v01));
-      gy = fadd(gy, -v02);
-      gy = fadd(gy, v20);
-      gy = fadd(gy, fadd(v21, v21));
-      gy = fadd(gy, v22);
-      m = __fsqrt_rn(fadd(fmul(gx, gx), fmul(gy, gy)));
-      // the direction is only ever read for centre pixels that pass the low threshold (suppressNonMaxima)
-      if (i >= 1 && i <= TH && j >= 1 && j <= TW) s_dir[i - 1][j - 1] = !(m < t_low) ? (uint8_t)direction_bin_fast(gy, gx) : (uint8_t)255;
-    } else if (i >= 1 && i <= TH && j >= 1 && j <= TW) {
-      s_dir[i - 1][j - 1] = 255;
-    }
-    s_mag[i][j] = m;
-  }
-  __syncthreads();
-  // 4. direction + non-maximum suppression for the TH x TW centre (suppressNonMaxima: interior pixels only)
+  // 2 + 3. blur and Sobel / magnitude / direction (see canny_blur_sobel)
+  if (r0 >= 3 && r0 + TH + 3 <= h && c0 >= 3 && c0 + TW + 3 <= w)
+    canny_blur_sobel<true>(s_gray, s_blur, s_mag, s_dir, tid, r0, c0, w, h, t_low);
+  else
+    canny_blur_sobel<false>(s_gray, s_blur, s_mag, s_dir, tid, r0, c0, w, h, t_low);
+  // 4. direction + non-maximum suppression for the TH x TW centre (suppressNonMaxima: interior pixels only); the
+  //    candidates (class > 0, a few percent of the pixels) are collected in a list for the hysteresis step
   for (int k = tid; k < TH * TW; k += 256) {
     int i = k / TW, j = k % TW;
     int r = r0 + i, c = c0 + j;
-    if (r >= h || c >= w) continue;
+    s_par[k] = k;
+    if (r >= h || c >= w) {
+      s_cls[i][j] = 0;
+      continue;
+    }
     uint8_t out = 0;
     if (r >= 1 && r < h - 1 && c >= 1 && c < w - 1) {
       float m = s_mag[i + 1][j + 1];
@@ -203,32 +227,31 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
     }
     s_cls[i][j] = out;
     cls[(size_t)seg * stride + (size_t)r * w + c] = out;
+    if (out) s_list[atomicAdd(&s_ncand, 1)] = (unsigned short)k;
   }
+  __syncthreads();
   // 5. hysteresis, tile-local part: 8-connected components of the candidates inside this tile are merged in shared
   //    memory; every candidate then points straight at its tile root (the smallest pixel index of its local component,
-  //    the same "larger under smaller" rule as the global merge), so k_uf_border only has to stitch tile borders.
-  for (int k = tid; k < TH * TW; k += 256) {
+  //    the same "larger under smaller" rule as the global merge -- so the result does not depend on the order of the list),
+  //    and k_uf_border only has to stitch tile borders.  One thread per (candidate, backward neighbour).
+  const int nc = s_ncand;
+  for (int q = tid; q < 4 * nc; q += 256) {
+    const int k = s_list[q >> 2], nb = q & 3;
     const int i = k / TW, j = k % TW;
-    s_par[k] = k;
-    if (r0 + i >= h || c0 + j >= w) s_cls[i][j] = 0;
-  }
-  __syncthreads();
-  for (int k = tid; k < TH * TW; k += 256) {
-    const int i = k / TW, j = k % TW;
-    if (!s_cls[i][j]) continue;
-    if (j > 0 && s_cls[i][j - 1]) uf_union(s_par, k, k - 1);
-    if (i > 0) {
-      if (j > 0 && s_cls[i - 1][j - 1]) uf_union(s_par, k, k - TW - 1);
-      if (s_cls[i - 1][j]) uf_union(s_par, k, k - TW);
-      if (j < TW - 1 && s_cls[i - 1][j + 1]) uf_union(s_par, k, k - TW + 1);
+    int other = -1;
+    if (nb == 0) {
+      if (j > 0 && s_cls[i][j - 1]) other = k - 1;
+    } else if (i > 0) {
+      const int jj = j + nb - 2;  // nb 1, 2, 3 -> columns j-1, j, j+1 of the row above
+      if (jj >= 0 && jj < TW && s_cls[i - 1][jj]) other = k - TW + nb - 2;
     }
+    if (other >= 0) uf_union(s_par, k, other);
   }
   __syncthreads();
-  for (int k = tid; k < TH * TW; k += 256) {
-    const int i = k / TW, j = k % TW;
-    if (!s_cls[i][j]) continue;
+  for (int q = tid; q < nc; q += 256) {
+    const int k = s_list[q];
     const int root = uf_find(s_par, k);
-    parent[(size_t)seg * stride + (size_t)(r0 + i) * w + (c0 + j)] = (r0 + root / TW) * w + (c0 + root % TW);
+    parent[(size_t)seg * stride + (size_t)(r0 + k / TW) * w + (c0 + k % TW)] = (r0 + root / TW) * w + (c0 + root % TW);
   }
 }
 
