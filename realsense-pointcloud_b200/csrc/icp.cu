@@ -27,6 +27,11 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int IT = 256;       // threads per CTA in k_icp_step
+// k_icp_rescan is latency-bound (dependent cell scans): four CTAs per SM (64 registers, a few spills) beat two at 128
+// registers by 22 % on the 50 M-point pair
+#ifndef RESCAN_MINB
+#define RESCAN_MINB 4
+#endif
 constexpr int NRED = 17;      // n, s(3), t(3), s t^T (9), sum d2
 
 struct IcpState {  // device-resident per pair
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(IT) k_icp_step(float4* __restrict__ work, cons
     int j = -1;
     float d2 = INFINITY;
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (BRUTE) {
+    if constexpr (BRUTE) {
       const float4* T = tgt + (size_t)tseg * tstride;
       for (int tb = 0; tb < nt; tb += IT) {
         __syncthreads();
@@ -666,17 +671,6 @@ __global__ void __launch_bounds__(SOLVE_T) k_icp_solve_peer(IcpState* __restrict
     if (lane < NRED) sums[lane] = v;
     __syncwarp();
     icp_solve_pair(&st[seg], sums, prm, n_active, lane);
-  }
-}
-
-__global__ void k_copy_work(const float4* __restrict__ src, const int* __restrict__ count, int stride_src,
-                            float4* __restrict__ work, int stride_work) {
-  const int seg = blockIdx.y;
-  const int n = count[seg];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float4 p = src[(size_t)seg * stride_src + i];
-    p.w = __int_as_float(i);  // original index (rgba is not needed by the iterations)
-    work[(size_t)seg * stride_work + i] = p;
   }
 }
 
@@ -1027,7 +1021,7 @@ __global__ void __launch_bounds__(1024) k_wl_offsets(const int* __restrict__ wlc
   if (tid == 0) wloff[seg * (nblk + 1) + nblk] = s_carry;
 }
 
-__global__ void __launch_bounds__(IT) k_icp_rescan(float4* __restrict__ work, const int* __restrict__ count, int stride,
+__global__ void __launch_bounds__(IT, RESCAN_MINB) k_icp_rescan(float4* __restrict__ work, const int* __restrict__ count, int stride,
                                                    const IcpState* __restrict__ st, DevGrid g, IcpDevParams prm,
                                                    float4* __restrict__ recB, const int* __restrict__ perm, int pstride,
                                                    const int* __restrict__ wl, const int* __restrict__ wloff,
