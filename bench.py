@@ -318,11 +318,14 @@ def ndt_config2_leg(ctx, R, gen_scene, guess, hbm_peak):
     s2, t2 = ctx.upload([v2[1]]), ctx.upload([v2[0]])
     p2 = R.ndt_params(resolution=0.05)
     R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
+    ms2 = 1e30
+    for _ in range(3):  # the align as a caller sees it (no profiling scopes inside), best of three
+        ctx.timer_start()
+        r2, _ = R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
+        ms2 = min(ms2, ctx.timer_stop())
     ctx.profile_reset()
-    ctx.profile(True)
-    ctx.timer_start()
-    r2, _ = R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
-    ms2 = ctx.timer_stop()
+    ctx.profile(True)  # per-kernel breakdown from one more, profiled align
+    R.ndt_align(ctx, s2, t2, p2, guess=guess, want_aligned=False)
     ctx.profile(False)
     ke, kc = ctx.profile_get("k_ndt_eval"), ctx.profile_get("k_ndt_control")
     kp = ctx.profile_get("k_ndt_persist")

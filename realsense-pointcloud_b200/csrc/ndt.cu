@@ -1697,10 +1697,11 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     LAUNCH_CHECK(ctx);
     rc = transform_device(ctx, src, d_T, 0, aligned);
   }
-  CU(ctx, ctx_sync(ctx));
   // source sizes for trans_probability = score / input_->size() (ndt.hpp); in point-sharded mode that is the size of the
   // WHOLE source, i.e. the shard counts summed over the ranks -- every rank then reports the same value
   std::vector<int> scnt(S);
+  if (!sharded) CU(ctx, small_d2h(ctx, scnt.data(), src->count, S * sizeof(int)));  // rides on the same synchronisation
+  CU(ctx, ctx_sync(ctx));
   if (sharded) {
     std::vector<double> cd(S);
     double* d_cnt = nullptr;
@@ -1713,9 +1714,6 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     CU(ctx, ctx_sync(ctx));
     scratch_free(ctx, d_cnt);
     for (int s = 0; s < S; ++s) scnt[s] = (int)(cd[s] + 0.5);
-  } else {
-    CU(ctx, small_d2h(ctx, scnt.data(), src->count, S * sizeof(int)));
-    CU(ctx, ctx_sync(ctx));
   }
   for (int s = 0; s < S; ++s) {
     memcpy(h_results[s].T, hst[s].final_T, 64);
