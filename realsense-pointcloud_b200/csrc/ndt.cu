@@ -1463,22 +1463,23 @@ int ndt_grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, const rspcl_ndt_param
   const long long N = (long long)S * pstride;
   G->inv_leaf = 1.0f / prm->resolution;
   G->r2 = (float)((double)prm->resolution * (double)prm->resolution);
+  Scratch scr(ctx);  // the temporaries; the grid itself (G->...) is owned by the caller (ndt_grid_free)
   unsigned long long *keys = nullptr, *tkeys = nullptr;
   int *vals = nullptr, *tvals = nullptr, *flags = nullptr, *ord = nullptr, *cell_start = nullptr, *leaf_flag = nullptr,
       *leaf_ord = nullptr, *n_cells = nullptr, *n_valid = nullptr;
-  CU(ctx, scratch_alloc(ctx, &keys, (size_t)N));
-  CU(ctx, scratch_alloc(ctx, &tkeys, (size_t)N));
-  CU(ctx, scratch_alloc(ctx, &vals, (size_t)N));
-  CU(ctx, scratch_alloc(ctx, &tvals, (size_t)N));
+  CU(ctx, scr.alloc(&keys, (size_t)N));
+  CU(ctx, scr.alloc(&tkeys, (size_t)N));
+  CU(ctx, scr.alloc(&vals, (size_t)N));
+  CU(ctx, scr.alloc(&tvals, (size_t)N));
   unsigned long long* flags_keys = nullptr;  // the one-CTA build's 64-bit keys at the cell heads
-  CU(ctx, scratch_alloc(ctx, &flags_keys, (size_t)N));
-  CU(ctx, scratch_alloc(ctx, &flags, (size_t)N));
-  CU(ctx, scratch_alloc(ctx, &ord, (size_t)N));
-  CU(ctx, scratch_alloc(ctx, &cell_start, (size_t)N + 1));
-  CU(ctx, scratch_alloc(ctx, &leaf_flag, (size_t)N));
-  CU(ctx, scratch_alloc(ctx, &leaf_ord, (size_t)N));
-  CU(ctx, scratch_alloc(ctx, &n_cells, 1));
-  CU(ctx, scratch_alloc(ctx, &n_valid, 1));
+  CU(ctx, scr.alloc(&flags_keys, (size_t)N));
+  CU(ctx, scr.alloc(&flags, (size_t)N));
+  CU(ctx, scr.alloc(&ord, (size_t)N));
+  CU(ctx, scr.alloc(&cell_start, (size_t)N + 1));
+  CU(ctx, scr.alloc(&leaf_flag, (size_t)N));
+  CU(ctx, scr.alloc(&leaf_ord, (size_t)N));
+  CU(ctx, scr.alloc(&n_cells, 1));
+  CU(ctx, scr.alloc(&n_valid, 1));
   CU(ctx, scratch_alloc(ctx, &G->n_leaves, 1));
   int nb = div_up(N, 256);
   if (nb > 16 * ctx->sm_count) nb = 16 * ctx->sm_count;
@@ -1530,18 +1531,7 @@ int ndt_grid_build(rspcl_ctx* ctx, const rspcl_cloud* tgt, const rspcl_ndt_param
   k_voxel_stats<<<nbw, 256, 0, ctx->stream>>>(tgt->pts, tgt->stride, pstride, head_keys, sorted_vals, cell_start, leaf_flag, leaf_ord, n_cells,
                                              prm->min_covar_eigvalue_mult, G->vox, G->hkeys, G->hvals, G->cap_mask, G->nvox_seg);
   LAUNCH_CHECK(ctx);
-  scratch_free(ctx, keys);
-  scratch_free(ctx, tkeys);
-  scratch_free(ctx, vals);
-  scratch_free(ctx, tvals);
-  scratch_free(ctx, flags_keys);
-  scratch_free(ctx, flags);
-  scratch_free(ctx, ord);
-  scratch_free(ctx, cell_start);
-  scratch_free(ctx, leaf_flag);
-  scratch_free(ctx, leaf_ord);
-  scratch_free(ctx, n_cells);
-  scratch_free(ctx, n_valid);
+  scr.ok();
   return RSPCL_OK;
 }
 
@@ -1582,9 +1572,15 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   double d1, d2;
   gauss_constants(prm->resolution, prm->outlier_ratio, &d1, &d2);
   int* d_range = nullptr;
-  CU(ctx, scratch_alloc(ctx, &d_range, 1));
+  Scratch scr(ctx);  // every temporary below; released on every exit path
+  CU(ctx, scr.alloc(&d_range, 1));
   CU(ctx, cudaMemsetAsync(d_range, 0, sizeof(int), ctx->stream));
   NdtGridDev G;
+  struct GridGuard {
+    rspcl_ctx* c;
+    NdtGridDev* g;
+    ~GridGuard() { ndt_grid_free(c, g); }
+  } grid_guard{ctx, &G};
   G.shared_target = shared_target;
   int rc;
   {
@@ -1599,14 +1595,14 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   int* n_active = nullptr;
   float* d_T = nullptr;
   const int nblk = blocks_per_seg(ctx, S, src->max_count_hint, NT);
-  CU(ctx, scratch_alloc(ctx, &st, (size_t)S));
-  CU(ctx, scratch_alloc(ctx, &ev, (size_t)S));
-  CU(ctx, scratch_alloc(ctx, &partials, (size_t)S * nblk * NACC));
-  CU(ctx, scratch_alloc(ctx, &n_active, 1));
-  CU(ctx, scratch_alloc(ctx, &d_T, (size_t)S * 16));
+  CU(ctx, scr.alloc(&st, (size_t)S));
+  CU(ctx, scr.alloc(&ev, (size_t)S));
+  CU(ctx, scr.alloc(&partials, (size_t)S * nblk * NACC));
+  CU(ctx, scr.alloc(&n_active, 1));
+  CU(ctx, scr.alloc(&d_T, (size_t)S * 16));
   const bool sharded = ctx->sharded_call && ctx->nccl_comm && ctx->nranks > 1;
   double* totals = nullptr;
-  if (sharded) CU(ctx, scratch_alloc(ctx, &totals, (size_t)S * NACC));
+  if (sharded) CU(ctx, scr.alloc(&totals, (size_t)S * NACC));
   CU(ctx, small_h2d(ctx, n_active, &S, sizeof(int)));
   k_ndt_init<<<div_up(S, 64), 64, 0, ctx->stream>>>(st, ev, d_guess, S);
   LAUNCH_CHECK(ctx);
@@ -1632,9 +1628,9 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       unsigned long long* d_work = nullptr;
       double* d_gpart = nullptr;
       int* d_fin = nullptr;
-      CU(ctx, scratch_alloc(ctx, &d_work, 2));
-      CU(ctx, scratch_alloc(ctx, &d_gpart, (size_t)2 * S * cpp * NACC));
-      CU(ctx, scratch_alloc(ctx, &d_fin, (size_t)S));
+      CU(ctx, scr.alloc(&d_work, 2));
+      CU(ctx, scr.alloc(&d_gpart, (size_t)2 * S * cpp * NACC));
+      CU(ctx, scr.alloc(&d_fin, (size_t)S));
       CU(ctx, cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned long long), ctx->stream));
       CU(ctx, cudaMemsetAsync(d_fin, 0x7F, (size_t)S * sizeof(int), ctx->stream));  // 0x7F7F7F7F: "not finished"
       const float4* a_src = src->pts;
@@ -1656,9 +1652,6 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
           prof.set_units((double)hw[0] + (double)hw[1] * (456.0 / 135.0));
         }
       }
-      scratch_free(ctx, d_work);
-      scratch_free(ctx, d_gpart);
-      scratch_free(ctx, d_fin);
       active = 0;
     }
   }
@@ -1705,14 +1698,13 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
   if (sharded) {
     std::vector<double> cd(S);
     double* d_cnt = nullptr;
-    CU(ctx, scratch_alloc(ctx, &d_cnt, (size_t)S));
+    CU(ctx, scr.alloc(&d_cnt, (size_t)S));
     k_counts_f64<<<div_up(S, 128), 128, 0, ctx->stream>>>(src->count, d_cnt, S);
     LAUNCH_CHECK(ctx);
     int rcc = comm_allreduce_f64(ctx, d_cnt, (size_t)S);
     if (rcc) return rcc;
     CU(ctx, small_d2h(ctx, cd.data(), d_cnt, (size_t)S * sizeof(double)));
     CU(ctx, ctx_sync(ctx));
-    scratch_free(ctx, d_cnt);
     for (int s = 0; s < S; ++s) scnt[s] = (int)(cd[s] + 0.5);
   }
   for (int s = 0; s < S; ++s) {
@@ -1725,16 +1717,9 @@ int ndt_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     h_results[s].trans_probability = hst[s].score / (double)(scnt[s] > 0 ? scnt[s] : 1);
     memcpy(h_results[s].p, hst[s].p, sizeof(double) * 6);
   }
-  ndt_grid_free(ctx, &G);
-  scratch_free(ctx, st);
-  scratch_free(ctx, ev);
-  scratch_free(ctx, partials);
-  scratch_free(ctx, n_active);
-  scratch_free(ctx, d_T);
-  scratch_free(ctx, d_range);
-  scratch_free(ctx, totals);
   if (rc) return rc;
   if (range) RSPCL_FAIL(ctx, RSPCL_ERR_RANGE, "ndt_align: target coordinates exceed the voxel key range");
+  scr.ok();
   return RSPCL_OK;
 }
 

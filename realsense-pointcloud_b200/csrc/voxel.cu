@@ -71,7 +71,8 @@ __device__ int block_excl_scan(int* data, int n, int* s_warp, int* s_carry) {
 
 __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ pts, const int* count,
                                                      int stride_in, float3 inv, int* __restrict__ sorted_all,
-                                                     int* __restrict__ ev_all, float4* __restrict__ out,
+                                                     float4* __restrict__ spt_all, int* __restrict__ ev_all,
+                                                     float4* __restrict__ out,
                                                      int* out_count, int stride_out,
                                                      int* __restrict__ overflow) {
   extern __shared__ int smem[];
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
   const int n = count[seg];
   const float4* P = pts + (size_t)seg * stride_in;
   int* sorted = sorted_all + (size_t)seg * stride_in;
+  float4* spt = spt_all + (size_t)seg * stride_in;  // the points in slot order: later phases stream it, no gathers
   int* ev = ev_all + (size_t)seg * stride_in;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (n == 0) {
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
     const bool act = i < w_hi;
     const unsigned amask = __ballot_sync(0xffffffffu, act);
     if (act) {
-      const unsigned s = vox_key(P[i], inv).slot;
+      const float4 pt = P[i];
+      const unsigned s = vox_key(pt, inv).slot;
       const unsigned peers = __match_any_sync(amask, s);
       const int leader = __ffs(peers) - 1;
       const int rank = __popc(peers & ((1u << lane) - 1u));
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
       }
       old = __shfl_sync(peers, old, leader);
       sorted[old + rank] = i;
+      spt[old + rank] = pt;
     }
     __syncwarp();
   }
@@ -143,14 +147,13 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
 
   // ---- 2. run heads; a head that is not the first point of its slot evicts the previous run
   for (int p = tid; p < n; p += VT) {
-    const int i = sorted[p];
-    const VoxKey k = vox_key(P[i], inv);
+    const VoxKey k = vox_key(spt[p], inv);
     int evict = 0;
     if (p != slot_start[k.slot]) {
-      const VoxKey kp = vox_key(P[sorted[p - 1]], inv);
+      const VoxKey kp = vox_key(spt[p - 1], inv);
       evict = (kp.ix != k.ix || kp.iy != k.iy || kp.iz != k.iz) ? 1 : 0;
     }
-    ev[i] = evict;
+    ev[sorted[p]] = evict;
   }
   __syncthreads();
   const int n_evict = block_excl_scan(ev, n, s_warp, s_misc);  // ev[i] := #evicting points before input index i
@@ -167,17 +170,16 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
   // ---- 3. one thread per run: sequential float sums in input order, then the flush arithmetic of PCL
   float4* O = out + (size_t)seg * stride_out;
   for (int p = tid; p < n; p += VT) {
-    const int i0 = sorted[p];
-    const VoxKey k = vox_key(P[i0], inv);
+    const VoxKey k = vox_key(spt[p], inv);
     const int s_lo = slot_start[k.slot], s_hi = slot_end[k.slot];
     if (p != s_lo) {
-      const VoxKey kp = vox_key(P[sorted[p - 1]], inv);
+      const VoxKey kp = vox_key(spt[p - 1], inv);
       if (kp.ix == k.ix && kp.iy == k.iy && kp.iz == k.iz) continue;  // not a run head
     }
     float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
     int cnt = 0, q = p, evictor = -1;
+    float4 pt = spt[q];
     while (true) {
-      const float4 pt = P[sorted[q]];
       const unsigned c = __float_as_uint(pt.w);
       sx = fadd(sx, pt.x);
       sy = fadd(sy, pt.y);
@@ -188,10 +190,10 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
       ++cnt;
       ++q;
       if (q >= s_hi) break;
-      const int j = sorted[q];
-      const VoxKey kn = vox_key(P[j], inv);
+      pt = spt[q];
+      const VoxKey kn = vox_key(pt, inv);
       if (kn.ix != k.ix || kn.iy != k.iy || kn.iz != k.iz) {
-        evictor = j;
+        evictor = sorted[q];
         break;
       }
     }
@@ -236,22 +238,25 @@ int voxel_approx_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float leaf[
   // per device and cheap: set on every call rather than caching a per-process flag (several devices per process)
   CU(ctx, cudaFuncSetAttribute(k_approx_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOX_SMEM));
   const size_t tot = (size_t)S * (in->stride ? in->stride : 1);
+  Scratch scr(ctx);  // released on every exit path
   int *sorted = nullptr, *ev = nullptr, *d_over = nullptr;
   float4* tmp = nullptr;
-  CU(ctx, scratch_alloc(ctx, &sorted, tot));
-  CU(ctx, scratch_alloc(ctx, &ev, tot));
-  CU(ctx, scratch_alloc(ctx, &d_over, 1));
+  float4* spt = nullptr;
+  CU(ctx, scr.alloc(&sorted, tot));
+  CU(ctx, scr.alloc(&spt, tot));
+  CU(ctx, scr.alloc(&ev, tot));
+  CU(ctx, scr.alloc(&d_over, 1));
   CU(ctx, cudaMemsetAsync(d_over, 0, sizeof(int), ctx->stream));
   const bool alias = (in == out);
   float4* obuf = out->pts;
   int ostride = out->stride;
   if (alias) {
-    CU(ctx, scratch_alloc(ctx, &tmp, tot));
+    CU(ctx, scr.alloc(&tmp, tot));
     obuf = tmp;
     ostride = in->stride;
   }
   ProfScope prof(ctx, "k_approx_voxel", (double)S * in->max_count_hint);
-  k_approx_voxel<<<S, VT, VOX_SMEM, ctx->stream>>>(in->pts, in->count, in->stride, inv, sorted, ev, obuf, out->count, ostride,
+  k_approx_voxel<<<S, VT, VOX_SMEM, ctx->stream>>>(in->pts, in->count, in->stride, inv, sorted, spt, ev, obuf, out->count, ostride,
                                                    d_over);
   LAUNCH_CHECK(ctx);
   if (alias) {
@@ -264,14 +269,11 @@ int voxel_approx_device(rspcl_ctx* ctx, const rspcl_cloud* in, const float leaf[
     CU(ctx, small_d2h(ctx, &over, d_over, sizeof(int)));
     CU(ctx, ctx_sync(ctx));
   }
-  scratch_free(ctx, sorted);
-  scratch_free(ctx, ev);
-  scratch_free(ctx, d_over);
-  scratch_free(ctx, tmp);
   if (over) RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "voxel_approx: output stride %d too small", out->stride);
   if (!alias) {
     out->max_count_hint = in->max_count_hint < out->stride ? in->max_count_hint : out->stride;
   }
+  scr.ok();
   out->width = out->height = 0;  // downsampling breaks the organized structure (PCL sets height = 1)
   return RSPCL_OK;
 }
