@@ -65,6 +65,47 @@ def test_voxel_gaussians_match_oracle(ctx, res):
         assert np.allclose(g["icov"][ok], exp["icov"][ok], rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("n,res", [(5, 1.0), (700, 0.25), (6000, 1.0), (6000, 0.2), (16384, 0.2), (16385, 0.25), (20000, 0.15),
+                                   (32768, 0.25), (40000, 0.25)])
+def test_single_target_voxel_build_all_size_classes(ctx, n, res):
+    """One target per call takes the one-CTA build (k_ndt_build_one): keys / sort in shared memory up to 16,384 points, in
+    global memory up to 32,768, the multi-kernel radix-sort path above that.  Same voxel records as the oracle in every class,
+    with non-finite points, a far outlier (wide cell box -> more key bits) and duplicates in the input."""
+    rng = np.random.default_rng(100 + n)
+    t = ndt_target(rng, n)
+    if n > 100:
+        t["x"][7:19] = np.nan
+        t["z"][n // 2] = np.inf
+        t["x"][3], t["y"][3], t["z"][3] = F(41.5), F(-77.25), F(13.0)  # outlier far from the room
+        t[40:60] = t[20:40]                                            # exact duplicates
+    prm_o, prm_g = orc.ndt_params(resolution=res), R.ndt_params(resolution=res)
+    g = R.ndt_voxels(ctx, ctx.upload([t]), prm_g)[0]
+    exp = orc.NdtGrid(t, prm_o).voxels()
+    assert len(g) == len(exp)
+    if n > 100:
+        assert len(exp) > 3
+    assert np.array_equal(g["ijk"], exp["ijk"]) and np.array_equal(g["npts"], exp["npts"])
+    assert np.array_equal(g["centroid"], exp["centroid"])
+    assert np.array_equal(g["mean"], exp["mean"])
+    assert np.array_equal(g["cov"], exp["cov"]) and np.array_equal(g["evals"], exp["evals"])  # same Jacobi, same bits
+    ok = exp["npts"] > 0
+    assert np.allclose(g["icov"][ok], exp["icov"][ok], rtol=1e-9, atol=1e-9)
+
+
+def test_single_target_voxel_build_degenerate_inputs(ctx):
+    prm_o, prm_g = orc.ndt_params(resolution=0.5), R.ndt_params(resolution=0.5)
+    rng = np.random.default_rng(9)
+    allnan = ndt_target(rng, 300)
+    allnan["y"][:] = np.nan
+    assert len(R.ndt_voxels(ctx, ctx.upload([allnan]), prm_g)[0]) == 0 == len(orc.NdtGrid(allnan, prm_o).voxels())
+    one_cell = rand_cloud(rng, 900, 0.05)  # every point in one or two cells around the origin
+    g, exp = R.ndt_voxels(ctx, ctx.upload([one_cell]), prm_g)[0], orc.NdtGrid(one_cell, prm_o).voxels()
+    assert len(g) == len(exp) >= 1 and np.array_equal(g["mean"], exp["mean"]) and np.array_equal(g["npts"], exp["npts"])
+    same = np.repeat(rand_cloud(rng, 1, 1.0), 64)  # 64 copies of one point: zero covariance
+    g, exp = R.ndt_voxels(ctx, ctx.upload([same]), prm_g)[0], orc.NdtGrid(same, prm_o).voxels()
+    assert len(g) == len(exp) == 1 and np.array_equal(g["npts"], exp["npts"]) and np.array_equal(g["mean"], exp["mean"])
+
+
 def test_voxel_gaussians_on_edge_clouds(ctx, sweep3):
     fr, _ = sweep3
     ec = edge_clouds(fr)
