@@ -58,6 +58,11 @@ __device__ __forceinline__ int direction_bin_fast(float gy, float gx) {
   return ((gy > 0.f) == (gx > 0.f)) ? 45 : 135;
 }
 
+// class byte written by k_canny_nms: bits 0-1 = 0 none / 1 weak / 2 strong; CLS_ROOT = the pixel is the root of its tile-local
+// component; CLS_LSTRONG (roots) = that local component holds a strong pixel; CLS_GSTRONG (roots, set by k_root_pull) = its
+// whole 8-connected component does
+constexpr unsigned CLS_LSTRONG = 4u, CLS_ROOT = 8u, CLS_GSTRONG = 16u;
+
 // ---- lock-free union-find over candidate pixels (per frame; parents are pixel indices within the frame)
 __device__ __forceinline__ int uf_find(volatile int* parent, int x) {
   int p = parent[x];
@@ -162,6 +167,7 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
   __shared__ uint8_t s_cls[TH][TW];
   __shared__ int s_par[TH * TW];  // tile-local union-find (parents are local pixel indices i * TW + j)
   __shared__ unsigned short s_list[TH * TW];  // the tile's candidates (any order)
+  __shared__ uint8_t s_strong[TH * TW];       // per tile root: its local component holds a strong pixel
   __shared__ int s_ncand;
   const int seg = blockIdx.z;
   const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH;
@@ -204,6 +210,7 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
     int i = k / TW, j = k % TW;
     int r = r0 + i, c = c0 + j;
     s_par[k] = k;
+    s_strong[k] = 0;
     if (r >= h || c >= w) {
       s_cls[i][j] = 0;
       continue;
@@ -248,15 +255,39 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
     if (other >= 0) uf_union(s_par, k, other);
   }
   __syncthreads();
-  for (int q = tid; q < nc; q += 256) {
-    const int k = s_list[q];
-    const int root = uf_find(s_par, k);
-    parent[(size_t)seg * stride + (size_t)(r0 + k / TW) * w + (c0 + k % TW)] = (r0 + root / TW) * w + (c0 + root % TW);
+  // every candidate records its tile root; a tile root is marked in its class byte (CLS_ROOT) together with "my local
+  // component holds a strong pixel" (CLS_LSTRONG).  From here on only tile roots take part in the union-find: a non-root
+  // candidate's parent is written once, here, and never touched again.
+  int roots[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int q = tid + m * 256;
+    roots[m] = -1;
+    if (q < nc) {
+      const int k = s_list[q];
+      roots[m] = uf_find(s_par, k);
+      if (s_cls[k / TW][k % TW] == 2) s_strong[roots[m]] = 1;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int q = tid + m * 256;
+    if (q < nc) {
+      const int k = s_list[q], root = roots[m];
+      const size_t gk = (size_t)seg * stride + (size_t)(r0 + k / TW) * w + (c0 + k % TW);
+      parent[gk] = (r0 + root / TW) * w + (c0 + root % TW);
+      if (root == k) cls[gk] = (uint8_t)(s_cls[k / TW][k % TW] | CLS_ROOT | (s_strong[k] ? CLS_LSTRONG : 0));
+    }
   }
 }
 
+// the tile root of candidate p (class byte cb): itself, or the parent k_canny_nms wrote (never modified afterwards)
+__device__ __forceinline__ int tile_root(const int* par, int p, unsigned cb) { return (cb & CLS_ROOT) ? p : par[p]; }
+
 // stitch the tile-local components across tile borders (the only unions left): candidates in the first row, first column
-// or last column of a k_canny_nms tile are united with their backward neighbours in global memory
+// or last column of a k_canny_nms tile are united with their backward neighbours in global memory -- through their TILE
+// ROOTS, so every path of the global forest runs over tile roots only
 __global__ void k_uf_border(const uint8_t* __restrict__ cls, int* __restrict__ parent, int w, int h, int stride) {
   const int seg = blockIdx.y;
   const uint8_t* c = cls + (size_t)seg * stride;
@@ -280,36 +311,79 @@ __global__ void k_uf_border(const uint8_t* __restrict__ cls, int* __restrict__ p
     const int r = ty * TH + i, col = tx * TW + j;
     if (r >= h || col >= w) continue;
     const int p = r * w + col;
-    if (!c[p]) continue;
-    // candidates are interior pixels, so the four backward neighbours are always in the image; unions with neighbours of
-    // the same tile are no-ops (already merged locally)
-    if (c[p - 1]) uf_union(par, p, p - 1);
-    if (c[p - w - 1]) uf_union(par, p, p - w - 1);
-    if (c[p - w]) uf_union(par, p, p - w);
-    if (c[p - w + 1]) uf_union(par, p, p - w + 1);
+    const unsigned cp = c[p];
+    if (!cp) continue;
+    // candidates are interior pixels, so the four backward neighbours are always in the image; neighbours of the same
+    // tile share the tile root (already merged locally)
+    const int rp = tile_root(par, p, cp);
+    const int nbr[4] = {p - 1, p - w - 1, p - w, p - w + 1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned cq = c[nbr[k]];
+      if (!cq) continue;
+      const int rq = tile_root(par, nbr[k], cq);
+      if (rq != rp) uf_union(par, rp, rq);
+    }
   }
 }
 
+// tile roots whose local component holds a strong pixel mark the root of their whole component
 __global__ void k_uf_flag(const uint8_t* __restrict__ cls, int* __restrict__ parent, uint8_t* __restrict__ strong, int n,
                           int stride) {
   const int seg = blockIdx.y;
   const uint8_t* c = cls + (size_t)seg * stride;
   int* par = parent + (size_t)seg * stride;
-  if ((stride & 3) == 0) {  // four class bytes per load: strong pixels are a fraction of a percent of the image
-    const unsigned* c4 = reinterpret_cast<const unsigned*>(c);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; 4 * q < n; q += gridDim.x * blockDim.x) {
-      unsigned wd = c4[q];
-      if (4 * q + 3 >= n) wd &= 0xFFFFFFFFu >> (8 * (4 * q + 4 - n));
-      // any byte == 2 ?  (classes are 0, 1, 2)
-      if (!(wd & 0x02020202u)) continue;
+  constexpr unsigned want = CLS_ROOT | CLS_LSTRONG;
+  if ((stride & 15) == 0) {  // sixteen class bytes per load: tile roots are ~0.3 % of the pixels
+    const uint4* c16 = reinterpret_cast<const uint4*>(c);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; 16 * q < n; q += gridDim.x * blockDim.x) {
+      const uint4 v = c16[q];
+      const unsigned wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (((wd >> (8 * k)) & 255u) == 2u) strong[(size_t)seg * stride + uf_find(par, 4 * q + k)] = 1;
+      for (int u = 0; u < 4; ++u) {
+        if (!(wd[u] & (wd[u] >> 1) & 0x04040404u)) continue;  // no byte with both bits
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 16 * q + 4 * u + k;
+          if ((((wd[u] >> (8 * k)) & want) == want) && i < n) strong[(size_t)seg * stride + uf_find(par, i)] = 1;
+        }
+      }
     }
     return;
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    if (c[i] == 2) strong[(size_t)seg * stride + uf_find(par, i)] = 1;
+    if ((c[i] & want) == want) strong[(size_t)seg * stride + uf_find(par, i)] = 1;
+}
+
+// ... and every tile root learns whether its whole component is strong (CLS_GSTRONG in its own class byte), so that
+// k_edge_mask needs two dependent loads per candidate and no pointer chase
+__global__ void k_root_pull(uint8_t* __restrict__ cls, int* __restrict__ parent, const uint8_t* __restrict__ strong, int n,
+                            int stride) {
+  const int seg = blockIdx.y;
+  uint8_t* c = cls + (size_t)seg * stride;
+  int* par = parent + (size_t)seg * stride;
+  if ((stride & 15) == 0) {
+    const uint4* c16 = reinterpret_cast<const uint4*>(c);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; 16 * q < n; q += gridDim.x * blockDim.x) {
+      const uint4 v = c16[q];
+      const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!(wd[u] & 0x08080808u)) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 16 * q + 4 * u + k;
+          const unsigned b = (wd[u] >> (8 * k)) & 255u;
+          if ((b & CLS_ROOT) && i < n && strong[(size_t)seg * stride + uf_find(par, i)]) c[i] = (uint8_t)(b | CLS_GSTRONG);
+        }
+      }
+    }
+    return;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned b = c[i];
+    if ((b & CLS_ROOT) && strong[(size_t)seg * stride + uf_find(par, i)]) c[i] = (uint8_t)(b | CLS_GSTRONG);
+  }
 }
 
 // pcl::OrganizedEdgeBase::extractEdges: NaN-boundary / occluding / occluded labels from the depth channel (the classes
@@ -385,35 +459,40 @@ constexpr int CB = 4 * CT;   // pixels per compaction block (four consecutive pi
 
 // mask = candidate whose component holds a strong pixel; per-block edge counts for the ordered compaction.  Four
 // consecutive pixels per thread: ~97 % of the class words are zero and cost one 32-bit load and one 32-bit store.
-__global__ void __launch_bounds__(CT) k_edge_mask(const uint8_t* __restrict__ cls, int* __restrict__ parent,
-                                                  const uint8_t* __restrict__ strong, uint8_t* __restrict__ mask,
-                                                  int* __restrict__ blk_cnt, int n, int stride, int nblk) {
+__global__ void __launch_bounds__(CT) k_edge_mask(const uint8_t* __restrict__ cls, const int* __restrict__ parent,
+                                                  uint8_t* __restrict__ mask, int* __restrict__ blk_cnt, int n, int stride,
+                                                  int nblk) {
   __shared__ int s_cnt;
   const int seg = blockIdx.y;
   const int i0 = blockIdx.x * CB + 4 * threadIdx.x;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   int cnt = 0;
+  const uint8_t* c = cls + (size_t)seg * stride;
+  const int* par = parent + (size_t)seg * stride;
+  // a candidate is an edge iff the component of its tile root is strong: its own byte if it is the root, else the root's
+  auto is_edge = [&](int i, unsigned b) -> bool {
+    if (!(b & 3u)) return false;
+    if (b & CLS_ROOT) return (b & CLS_GSTRONG) != 0;
+    return (c[par[i]] & CLS_GSTRONG) != 0;
+  };
   if (i0 < n) {
     const size_t g0 = (size_t)seg * stride + i0;
     if ((stride & 3) == 0 && i0 + 3 < n) {
       const unsigned wd = *reinterpret_cast<const unsigned*>(cls + g0);
       unsigned out = 0u;
-      if (wd) {
+      if (wd & 0x03030303u) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if ((wd >> (8 * k)) & 255u) {
-            if (strong[(size_t)seg * stride + uf_find(parent + (size_t)seg * stride, i0 + k)]) {
-              out |= 255u << (8 * k);
-              ++cnt;
-            }
+          if (is_edge(i0 + k, (wd >> (8 * k)) & 255u)) {
+            out |= 255u << (8 * k);
+            ++cnt;
           }
       }
       *reinterpret_cast<unsigned*>(mask + g0) = out;
     } else {
       for (int k = 0; k < 4 && i0 + k < n; ++k) {
-        int e = 0;
-        if (cls[g0 + k]) e = strong[(size_t)seg * stride + uf_find(parent + (size_t)seg * stride, i0 + k)] ? 1 : 0;
+        const int e = is_edge(i0 + k, c[i0 + k]) ? 1 : 0;
         mask[g0 + k] = e ? 255 : 0;
         cnt += e;
       }
@@ -588,8 +667,10 @@ static int edge_extract_impl(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_
   LAUNCH_CHECK(ctx);
   k_uf_flag<<<g2, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);
   LAUNCH_CHECK(ctx);
+  k_root_pull<<<g2, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);
+  LAUNCH_CHECK(ctx);
   dim3 g3(nblk, S);
-  k_edge_mask<<<g3, CT, 0, ctx->stream>>>(cls, parent, strong, mask, blk, n, stride, nblk);
+  k_edge_mask<<<g3, CT, 0, ctx->stream>>>(cls, parent, mask, blk, n, stride, nblk);
   LAUNCH_CHECK(ctx);
   k_seg_scan<<<S, 1024, 0, ctx->stream>>>(blk, nblk, out_edges->count, out_edges->stride, d_over);
   LAUNCH_CHECK(ctx);
