@@ -454,7 +454,7 @@ __global__ void k_or_mask(const uint8_t* __restrict__ mask, uint8_t* __restrict_
     if (mask[(size_t)seg * stride + i]) labels[(size_t)seg * stride + i] |= 16;  // EDGELABEL_RGB_CANNY
 }
 
-constexpr int CT = 1024;      // threads per compaction block
+constexpr int CT = 256;       // threads per compaction block
 constexpr int CB = 4 * CT;   // pixels per compaction block (four consecutive pixels per thread)
 
 // mask = candidate whose component holds a strong pixel; per-block edge counts for the ordered compaction.  Four
