@@ -663,11 +663,15 @@ static int edge_extract_impl(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_
   }
   dim3 g2(blocks_per_seg(ctx, S, n, 256), S);
   ProfScope prof_h(ctx, "edge_hysteresis_compact", (double)S * n);
-  k_uf_border<<<g2, 256, 0, ctx->stream>>>(cls, parent, w, h, stride);
+  // latency-bound scans (one dependent chain per hit): one item per thread, no grid-stride loop, so that as many chains as
+  // possible are in flight
+  const long long border_items = (long long)div_up(w, TW) * div_up(h, TH) * (TW + 2 * (TH - 1));
+  dim3 gb((unsigned)div_up(border_items, 256), S), gf((unsigned)div_up(div_up(n, 16), 256), S);
+  k_uf_border<<<gb, 256, 0, ctx->stream>>>(cls, parent, w, h, stride);
   LAUNCH_CHECK(ctx);
-  k_uf_flag<<<g2, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);
+  k_uf_flag<<<gf, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);
   LAUNCH_CHECK(ctx);
-  k_root_pull<<<g2, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);
+  k_root_pull<<<gf, 256, 0, ctx->stream>>>(cls, parent, strong, n, stride);
   LAUNCH_CHECK(ctx);
   dim3 g3(nblk, S);
   k_edge_mask<<<g3, CT, 0, ctx->stream>>>(cls, parent, mask, blk, n, stride, nblk);
