@@ -147,20 +147,26 @@ __device__ __forceinline__ int grid_nn_top2(const DevGrid& g, int seg, float qx,
   float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
   if (grid_in_range(x0, y0, z0) && grid_in_range(x1, y1, z1)) {
     const int tseg = g.shared_target ? 0 : seg;
-    GridSlot sl[8];
-    unsigned long long keys[8];
-    unsigned hs[8];
+    // two halves of four cells (z0 then z1): half the slot / key registers of an eight-wide probe -- the callers are
+    // latency-bound and run at four CTAs per SM, where registers are what limits the loads in flight
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+    if (half && z1 == z0) break;
+    const int iz = half ? z1 : z0;
+    GridSlot sl[4];
+    unsigned long long keys[4];
+    unsigned hs[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const bool dup = ((c & 1) && x1 == x0) || ((c & 2) && y1 == y0) || ((c & 4) && z1 == z0);
-      const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0, iz = (c & 4) ? z1 : z0;
+    for (int c = 0; c < 4; ++c) {
+      const bool dup = ((c & 1) && x1 == x0) || ((c & 2) && y1 == y0);
+      const int ix = (c & 1) ? x1 : x0, iy = (c & 2) ? y1 : y0;
       keys[c] = dup ? GRID_EMPTY : grid_key(tseg, ix, iy, iz);
       hs[c] = grid_hash4(tseg, ix, iy, iz) & g.cap_mask;
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sl[c] = grid_load_slot(&g.slots[hs[c]]);
+    for (int c = 0; c < 4; ++c) sl[c] = grid_load_slot(&g.slots[hs[c]]);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       if (keys[c] == GRID_EMPTY) continue;
       GridSlot s = sl[c];
       if (s.key != keys[c]) {
@@ -184,6 +190,7 @@ __device__ __forceinline__ int grid_nn_top2(const DevGrid& g, int seg, float qx,
           d2nd = fminf(d2nd, d);
         }
       }
+    }
     }
   }
   *out_d2 = bd;

@@ -1027,6 +1027,9 @@ __global__ void __launch_bounds__(IT, RESCAN_MINB) k_icp_rescan(float4* __restri
                                                    const int* __restrict__ wl, const int* __restrict__ wloff,
                                                    double* __restrict__ partials, int* __restrict__ corr_out, int corr_iters) {
   __shared__ double s_red[IT / 32][NRED];
+  // the 17 running sums of every thread live in shared memory ([sum][thread]: conflict-free), not in 34 registers: the
+  // kernel is latency-bound and runs at four CTAs per SM, where registers are what limits the probes in flight
+  __shared__ double s_acc[NRED][IT];
   const int seg = blockIdx.y;
   if (st[seg].done) return;
   const int n = count[seg];
@@ -1038,9 +1041,8 @@ __global__ void __launch_bounds__(IT, RESCAN_MINB) k_icp_rescan(float4* __restri
   const int* off = wloff + seg * (nblk + 1);
   const int total = off[nblk];
   const float r = prm.search_r;
-  double acc[NRED];
 #pragma unroll
-  for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+  for (int k = 0; k < NRED; ++k) s_acc[k][threadIdx.x] = 0.0;
   // item t of the segment's concatenated (block-ordered) work list: a fixed item -> thread map, so sums stay reproducible
   for (int t_ = blockIdx.x * IT + threadIdx.x; t_ < total; t_ += nblk * IT) {
     int lo_b = 0, hi_b = nblk;  // largest b with off[b] <= t_
@@ -1059,11 +1061,18 @@ __global__ void __launch_bounds__(IT, RESCAN_MINB) k_icp_rescan(float4* __restri
     recB[gi] = make_float4(t.x, t.y, t.z, __int_as_float(pos));
     const bool ok = best >= 0 && !((double)bd > prm.max_dist_sqr);
     if (want_corr) first_corr[(size_t)seg * stride + perm[(size_t)seg * pstride + i]] = ok ? best : -1;
-    if (ok) icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
+    if (ok) {
+      double acc[NRED];
+#pragma unroll
+      for (int k = 0; k < NRED; ++k) acc[k] = s_acc[k][threadIdx.x];
+      icp_accumulate(acc, p.x, p.y, p.z, t.x, t.y, t.z, bd);
+#pragma unroll
+      for (int k = 0; k < NRED; ++k) s_acc[k][threadIdx.x] = acc[k];
+    }
   }
 #pragma unroll
   for (int k = 0; k < NRED; ++k) {
-    const double v = warp_sum(acc[k]);
+    const double v = warp_sum(s_acc[k][threadIdx.x]);
     if (lane == 0) s_red[wid][k] = v;
   }
   __syncthreads();
