@@ -9,9 +9,10 @@
 //   K1  k_canny_nms   gray -> 3x3 Gaussian (9-tap, clamp) -> Sobel (clamp) -> sqrtf magnitude -> direction bin
 //                     -> non-maximum suppression, fused over a shared-memory halo tile; writes a 1-byte class
 //                     (0 none, 1 weak >= t_low, 2 strong >= t_high) and seeds the union-find parents.
-//   K1b (in k_canny_nms) + k_uf_border / k_uf_flag / k_edge_mask   hysteresis as 8-connected components of {class>0}
-//                     that contain a strong pixel: lock-free union-find, tile-local in shared memory inside K1, stitched
-//                     across tile borders in global memory (the result is order-independent, so it is exact).
+//   K1b (in k_canny_nms) + k_uf_border / k_uf_flag / k_root_pull / k_edge_mask   hysteresis as 8-connected components of
+//                     {class>0} that contain a strong pixel: lock-free union-find, tile-local in shared memory inside K1,
+//                     stitched across tile borders in global memory over the TILE ROOTS only (the result is
+//                     order-independent, so it is exact); the roots carry the strong flags in their class byte.
 //   K1c k_block_count / k_seg_scan / k_scatter  mask -> ascending row-major compaction (copyPointCloud(indices)).
 // Roofline: HBM-bound; algorithmic bytes per pixel = 1 R (gray) + 1 W (class) for K1.
 #include "common.cuh"
