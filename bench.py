@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-configs0", action="store_true", help="skip the literal rs-pcl --registration leg (configs[0])")
     ap.add_argument("--no-sharded", action="store_true", help="skip the point-sharded leg (configs[4])")
     ap.add_argument("--no-batch", action="store_true", help="skip the 4096-pair batch leg (configs[4])")
+    ap.add_argument("--distinct-sweeps", action="store_true", help="N > 1: a different synthetic sweep (seed + 1000 rank) per rank instead of the same one")
     ap.add_argument("--batch-pairs", type=int, default=4096)
     ap.add_argument("--sharded-points", type=int, default=50_000_000, help="points of the source AND of the target of the point-sharded leg")
     ap.add_argument("--sharded-iters", type=int, default=30)
@@ -100,14 +101,15 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, all_devices=None):
         self.device = device
+        self.all = list(all_devices) if all_devices else [device]  # N > 1: rank 0 watches every GPU of the job
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(d) for d in self.all), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -128,21 +130,27 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, per = [], [], set(), {}
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
+                idx, clk = int(f[0]), float(f[1])
                 mx.append(float(f[2]))
             except ValueError:
                 continue
+            per.setdefault(idx, []).append(clk)
+            if idx == self.device:
+                sm.append(clk)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if len(per) > 1:
+            out["per_gpu_sm_mhz"] = {str(k): float(np.median(v)) for k, v in sorted(per.items())}
+        return out
 
 
 # ---------------------------------------------------------------------------------------------- CPU (oracle) legs
@@ -243,7 +251,9 @@ def workload_config(a, frames):
             "frames_per_gpu": frames, "pairs_per_step_per_gpu": frames - 1, "points_per_frame": NPX,
             "coarse": a.coarse, "icp_iterations": [a.iters, a.iters],
             "l2": "inputs larger than L2 (%.0f MB of frames per step vs 126 MB L2)" % (frames * NPX * 16 / 1e6),
-            "parallelism": "pair-sharded x%d (independent sweeps, no collective)" % a.gpus}
+            "parallelism": "pair-sharded x%d (one independent sweep per rank, no collective)" % a.gpus,
+            "per_rank_data": ("a different synthetic sweep per rank (seed + 1000 rank)" if a.distinct_sweeps else
+                              "the same synthetic sweep on every rank: fixed work per GPU (weak scaling)")}
 
 
 def bind_to_gpu_numa_node(torch, dev):
@@ -261,6 +271,15 @@ def bind_to_gpu_numa_node(torch, dev):
             elif part:
                 cpus.add(int(part))
         allowed = os.sched_getaffinity(0)
+        if os.environ.get("BENCH_PIN") == "1":  # diagnostic: a private pair of CPUs per rank
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            rank = int(os.environ.get("LOCAL_RANK", "0"))
+            al = sorted(allowed)
+            per = max(1, len(al) // max(world, 1))
+            mine = set(al[rank * per:(rank + 1) * per])
+            if mine:
+                os.sched_setaffinity(0, mine)
+                return "pinned to CPUs %s (BENCH_PIN)" % sorted(mine)
         use = cpus & allowed
         if use and use != allowed:
             os.sched_setaffinity(0, use)
@@ -614,7 +633,9 @@ def main():
 
     F = a.frames
     n_pairs = F - 1
-    frames, Tgt = gen_scene.make_sweep(a.seed + 1000 * rank, F)
+    # weak scaling = fixed work per GPU: every rank registers the SAME synthetic sweep unless --distinct-sweeps is given
+    # (different scene content costs 1.98 - 2.73 ms per step, and the slowest rank is what gets reported: measured at N = 8)
+    frames, Tgt = gen_scene.make_sweep(a.seed + (1000 * rank if a.distinct_sweeps else 0), F)
     guess = guess_matrix()
     icp = R.icp_params(**forced_kw(a.iters))
     ndt = R.ndt_params()
@@ -678,7 +699,7 @@ def main():
     for _ in range(a.warmup):
         step()
     barrier()
-    sampler = ClockSampler(dev)
+    sampler = ClockSampler(dev, range(world) if world > 1 else None)
     if rank == 0:
         sampler.start()
     l0 = ctx.launches()
@@ -688,6 +709,11 @@ def main():
     ms = ctx.timer_stop()
     l1 = ctx.launches()
     barrier()
+    ms_rank = [ms]
+    if dist is not None:
+        t_all = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(t_all, torch.tensor([ms], dtype=torch.float64, device="cuda"))
+        ms_rank = [float(t.item()) for t in t_all]
     ms = max_over_ranks(ms)
     value = world * n_pairs * a.steps / (ms / 1e3)
 
@@ -880,7 +906,8 @@ def main():
                       "download_probe_one_chunk": probe})
         out = {
             "metric": "frame-pair registrations/sec @640x480", "value": value, "unit": "pairs/s", "n_gpus": world,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "ms_per_step_per_rank": [m / a.steps for m in ms_rank],
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, F),
             "clocks": clocks,

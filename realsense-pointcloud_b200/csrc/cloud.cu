@@ -77,7 +77,19 @@ cudaError_t small_d2h(rspcl_ctx* ctx, void* h_dst, const void* d_src, size_t byt
 }
 
 cudaError_t ctx_sync(rspcl_ctx* ctx) {
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  // RSPCL_SYNC=spin: poll the stream instead of sleeping in the driver (a host round trip sits on the critical path of
+  // every registration call: edge counts, persistent-kernel status)
+  static const int spin = [] {
+    const char* e = getenv("RSPCL_SYNC");
+    return (e && e[0] == 's') ? 1 : 0;
+  }();
+  cudaError_t e = cudaSuccess;
+  if (spin) {
+    while ((e = cudaStreamQuery(ctx->stream)) == cudaErrorNotReady) {
+    }
+  } else {
+    e = cudaStreamSynchronize(ctx->stream);
+  }
   if (e != cudaSuccess) return e;
   for (auto& p : ctx->z_pending) {
     memcpy(p.dst, p.src, p.n);
