@@ -456,18 +456,18 @@ __global__ void k_or_mask(const uint8_t* __restrict__ mask, uint8_t* __restrict_
 }
 
 constexpr int CT = 256;       // threads per compaction block
-constexpr int CB = 4 * CT;   // pixels per compaction block (four consecutive pixels per thread)
+constexpr int CPT = 16;       // consecutive pixels per thread (one 128-bit word of class / mask bytes)
+constexpr int CB = CPT * CT;  // pixels per compaction block
 
-// mask = candidate whose component holds a strong pixel; per-block edge counts for the ordered compaction.  Four
-// consecutive pixels per thread: ~97 % of the class words are zero and cost one 32-bit load and one 32-bit store.
+// mask = candidate whose component holds a strong pixel; per-block edge counts for the ordered compaction.  Sixteen
+// consecutive pixels per thread: ~97 % of the class words are zero, and these kernels are bound by the bytes (and the
+// dependent loads of the few candidates) in flight, not by bandwidth.
 __global__ void __launch_bounds__(CT) k_edge_mask(const uint8_t* __restrict__ cls, const int* __restrict__ parent,
                                                   uint8_t* __restrict__ mask, int* __restrict__ blk_cnt, int n, int stride,
                                                   int nblk) {
-  __shared__ int s_cnt;
+  __shared__ int s_w[CT / 32];
   const int seg = blockIdx.y;
-  const int i0 = blockIdx.x * CB + 4 * threadIdx.x;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
+  const int i0 = blockIdx.x * CB + CPT * threadIdx.x;
   int cnt = 0;
   const uint8_t* c = cls + (size_t)seg * stride;
   const int* par = parent + (size_t)seg * stride;
@@ -479,20 +479,23 @@ __global__ void __launch_bounds__(CT) k_edge_mask(const uint8_t* __restrict__ cl
   };
   if (i0 < n) {
     const size_t g0 = (size_t)seg * stride + i0;
-    if ((stride & 3) == 0 && i0 + 3 < n) {
-      const unsigned wd = *reinterpret_cast<const unsigned*>(cls + g0);
-      unsigned out = 0u;
-      if (wd & 0x03030303u) {
+    if ((stride & 15) == 0 && i0 + CPT - 1 < n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(cls + g0);
+      const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+      unsigned out[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!(wd[u] & 0x03030303u)) continue;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (is_edge(i0 + k, (wd >> (8 * k)) & 255u)) {
-            out |= 255u << (8 * k);
+          if (is_edge(i0 + 4 * u + k, (wd[u] >> (8 * k)) & 255u)) {
+            out[u] |= 255u << (8 * k);
             ++cnt;
           }
       }
-      *reinterpret_cast<unsigned*>(mask + g0) = out;
+      *reinterpret_cast<uint4*>(mask + g0) = make_uint4(out[0], out[1], out[2], out[3]);
     } else {
-      for (int k = 0; k < 4 && i0 + k < n; ++k) {
+      for (int k = 0; k < CPT && i0 + k < n; ++k) {
         const int e = is_edge(i0 + k, c[i0 + k]) ? 1 : 0;
         mask[g0 + k] = e ? 255 : 0;
         cnt += e;
@@ -500,9 +503,14 @@ __global__ void __launch_bounds__(CT) k_edge_mask(const uint8_t* __restrict__ cl
     }
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
-  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);  // integer sum: order does not matter
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
   __syncthreads();
-  if (threadIdx.x == 0) blk_cnt[seg * nblk + blockIdx.x] = s_cnt;
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < CT / 32; ++w) t += s_w[w];
+    blk_cnt[seg * nblk + blockIdx.x] = t;
+  }
 }
 
 // one CTA per frame: exclusive scan of its block counts (nblk <= a few thousand), writes the frame's edge count
@@ -556,20 +564,23 @@ __global__ void __launch_bounds__(1024) k_seg_scan(int* __restrict__ blk_cnt, in
 __global__ void __launch_bounds__(CT) k_scatter(const uint8_t* __restrict__ mask, const int* __restrict__ blk_off,
                                                 const float4* __restrict__ pts, const int* __restrict__ out_count,
                                                 float4* __restrict__ out, int n, int stride, int out_stride, int nblk) {
-  __shared__ int warp_tot[32];
+  __shared__ int warp_tot[CT / 32];
   const int seg = blockIdx.y;
   if (out_count[seg] == 0) return;  // empty or overflowed frame
-  const int i0 = blockIdx.x * CB + 4 * threadIdx.x;
+  const int i0 = blockIdx.x * CB + CPT * threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned flags = 0u;  // bit k: pixel i0 + k is an edge
   if (i0 < n) {
     const size_t g0 = (size_t)seg * stride + i0;
-    if ((stride & 3) == 0 && i0 + 3 < n) {
-      const unsigned wd = *reinterpret_cast<const unsigned*>(mask + g0);
+    if ((stride & 15) == 0 && i0 + CPT - 1 < n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(mask + g0);
+      const unsigned wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) flags |= ((wd >> (8 * k)) & 255u) ? (1u << k) : 0u;
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) flags |= ((wd[u] >> (8 * k)) & 255u) ? (1u << (4 * u + k)) : 0u;
     } else {
-      for (int k = 0; k < 4 && i0 + k < n; ++k) flags |= mask[g0 + k] ? (1u << k) : 0u;
+      for (int k = 0; k < CPT && i0 + k < n; ++k) flags |= mask[g0 + k] ? (1u << k) : 0u;
     }
   }
   const int c = __popc(flags);
@@ -581,21 +592,15 @@ __global__ void __launch_bounds__(CT) k_scatter(const uint8_t* __restrict__ mask
   }
   if (lane == 31) warp_tot[wid] = incl;
   __syncthreads();
-  if (wid == 0) {
-    int wv = warp_tot[lane], wi = wv;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += t;
-    }
-    warp_tot[lane] = wi - wv;
-  }
-  __syncthreads();
   if (flags) {  // ascending pixel order: block offset + warps before + lanes before + own earlier pixels
-    int pos = blk_off[seg * nblk + blockIdx.x] + warp_tot[wid] + incl - c;
+    int pos = blk_off[seg * nblk + blockIdx.x] + incl - c;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (flags & (1u << k)) out[(size_t)seg * out_stride + pos++] = pts[(size_t)seg * stride + i0 + k];
+    for (int w = 0; w < CT / 32; ++w) pos += (w < wid) ? warp_tot[w] : 0;
+    while (flags) {
+      const int k = __ffs(flags) - 1;
+      flags &= flags - 1;
+      out[(size_t)seg * out_stride + pos++] = pts[(size_t)seg * stride + i0 + k];
+    }
   }
 }
 

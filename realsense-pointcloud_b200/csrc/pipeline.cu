@@ -47,16 +47,27 @@ __global__ void k_transform2_gather(const float4* __restrict__ frames, int w_h, 
   if (blockIdx.x == 0 && threadIdx.x == 0) out_count[seg] = ok ? w_h : 0;
   if (!ok) return;
   const float4* F = frames + (size_t)src_idx[seg] * in_stride;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w_h; i += gridDim.x * blockDim.x) {
-    float4 p = F[i];
-    if (finite3(p.x, p.y, p.z)) {
-      float3 q = xform_point(A, p.x, p.y, p.z);
-      q = xform_point(B, q.x, q.y, q.z);
-      p.x = q.x;
-      p.y = q.y;
-      p.z = q.z;
+  float4* O = out + (size_t)seg * out_stride;
+  const int G = gridDim.x * blockDim.x;
+  // four points per trip, all four loads issued before the first use (HBM-bound: bytes in flight are what counts)
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < w_h; i0 += 4 * G) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * G < w_h) p[u] = __ldcs(&F[i0 + u * G]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * G >= w_h) break;
+      float4 v = p[u];
+      if (finite3(v.x, v.y, v.z)) {
+        float3 q = xform_point(A, v.x, v.y, v.z);
+        q = xform_point(B, q.x, q.y, q.z);
+        v.x = q.x;
+        v.y = q.y;
+        v.z = q.z;
+      }
+      __stcs(&O[i0 + u * G], v);
     }
-    out[(size_t)seg * out_stride + i] = p;
   }
 }
 
