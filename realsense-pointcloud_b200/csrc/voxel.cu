@@ -32,15 +32,19 @@ __device__ __forceinline__ VoxKey vox_key(float4 p, float3 inv) {
   return k;
 }
 
-// block-wide exclusive scan of data[0..n) in place (global or shared), returns the total to every thread
+// block-wide exclusive scan of data[0..n) in place (global or shared), returns the total to every thread.  Four
+// consecutive elements per thread and round: a quarter of the rounds (and barriers) of a one-element scan.
 __device__ int block_excl_scan(int* data, int n, int* s_warp, int* s_carry) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) *s_carry = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += VT) {
-    int i = base + threadIdx.x;
-    int v = i < n ? data[i] : 0;
-    int incl = v;
+  for (int base = 0; base < n; base += 4 * VT) {
+    const int i = base + 4 * threadIdx.x;
+    int v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i + u < n) ? data[i + u] : 0;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -58,10 +62,14 @@ __device__ int block_excl_scan(int* data, int n, int* s_warp, int* s_carry) {
       s_warp[lane] = wi - wv;
     }
     __syncthreads();
-    int excl = *s_carry + s_warp[wid] + incl - v;
-    if (i < n) data[i] = excl;
+    int run = *s_carry + s_warp[wid] + incl - mine;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i + u < n) data[i + u] = run;
+      run += v[u];
+    }
     __syncthreads();
-    if (threadIdx.x == VT - 1) *s_carry = excl + v;
+    if (threadIdx.x == VT - 1) *s_carry = run;
     __syncthreads();
   }
   const int total = *s_carry;
@@ -99,7 +107,15 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
   // ---- 1a. warp-private histograms over contiguous slices
   const int L = (n + VW - 1) / VW;
   const int w_lo = min(wid * L, n), w_hi = min(w_lo + L, n);
-  for (int i = w_lo + lane; i < w_hi; i += 32) atomicAdd(&hist[wid * NSLOT + vox_key(P[i], inv).slot], 1);
+  for (int i = w_lo + lane; i < w_hi; i += 128) {  // four loads in flight per lane
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + 32 * u < w_hi) q[u] = P[i + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + 32 * u < w_hi) atomicAdd(&hist[wid * NSLOT + vox_key(q[u], inv).slot], 1);
+  }
   __syncthreads();
   // ---- 1b. slot totals -> slot offsets -> per-(warp,slot) write cursors
   if (tid < NSLOT) {
@@ -122,12 +138,14 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
   }
   __syncthreads();
   // ---- 1c. stable scatter: each warp walks its slice in order, 32 points at a time
+  float4 nxt = (w_lo + lane < w_hi) ? P[w_lo + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int base = w_lo; base < w_hi; base += 32) {
     const int i = base + lane;
     const bool act = i < w_hi;
     const unsigned amask = __ballot_sync(0xffffffffu, act);
+    const float4 pt = nxt;
+    if (i + 32 < w_hi) nxt = P[i + 32];  // the next trip's point is on its way while this one is ranked
     if (act) {
-      const float4 pt = P[i];
       const unsigned s = vox_key(pt, inv).slot;
       const unsigned peers = __match_any_sync(amask, s);
       const int leader = __ffs(peers) - 1;
@@ -145,15 +163,32 @@ __global__ void __launch_bounds__(VT) k_approx_voxel(const float4* __restrict__ 
   }
   __syncthreads();  // (block-scope barrier also orders the global writes to sorted[] for this CTA)
 
-  // ---- 2. run heads; a head that is not the first point of its slot evicts the previous run
-  for (int p = tid; p < n; p += VT) {
-    const VoxKey k = vox_key(spt[p], inv);
-    int evict = 0;
-    if (p != slot_start[k.slot]) {
-      const VoxKey kp = vox_key(spt[p - 1], inv);
-      evict = (kp.ix != k.ix || kp.iy != k.iy || kp.iz != k.iz) ? 1 : 0;
+  // ---- 2. run heads; a head that is not the first point of its slot evicts the previous run (four positions per trip,
+  //         every load of the trip issued before the first use)
+  for (int p0 = tid; p0 < n; p0 += 4 * VT) {
+    float4 a[4], b[4];
+    int si[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * VT;
+      if (p < n) {
+        a[u] = spt[p];
+        b[u] = spt[p > 0 ? p - 1 : 0];
+        si[u] = sorted[p];
+      }
     }
-    ev[sorted[p]] = evict;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * VT;
+      if (p >= n) break;
+      const VoxKey k = vox_key(a[u], inv);
+      int evict = 0;
+      if (p != slot_start[k.slot]) {
+        const VoxKey kp = vox_key(b[u], inv);
+        evict = (kp.ix != k.ix || kp.iy != k.iy || kp.iz != k.iz) ? 1 : 0;
+      }
+      ev[si[u]] = evict;
+    }
   }
   __syncthreads();
   const int n_evict = block_excl_scan(ev, n, s_warp, s_misc);  // ev[i] := #evicting points before input index i
