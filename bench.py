@@ -717,6 +717,18 @@ def main():
     ms = max_over_ranks(ms)
     value = world * n_pairs * a.steps / (ms / 1e3)
 
+    # ---- roofline of the dominant kernel, from per-launch CUDA events in one extra profiled step (taken right after the
+    # timed region: the e2e legs below run several contexts side by side on this GPU, which is a different regime)
+    ctx.profile_reset()
+    ctx.profile(True)
+    ctx.timer_start()
+    step()
+    ms_prof = ctx.timer_stop()
+    ctx.profile(False)
+    prof_snapshot = {k: ctx.profile_get(k) for k in ("k_icp_persist", "k_icp_step", "k_icp_stream", "k_icp_rescan", "k_icp_solve", "grid_build",
+                                                     "k_canny_nms", "edge_hysteresis_compact", "k_approx_voxel", "k_transform2",
+                                                     "k_ndt_eval", "ndt_voxel_build")}
+
     # ---- end to end through the C ABI with host buffers: the sweep is cut into chunks of pairs that are pipelined over
     # several contexts (one stream + one host thread each), so chunk c+1's H2D, chunk c's kernels and chunk c-1's D2H
     # overlap (PCIe is full duplex).  Every frame still crosses PCIe (a chunk re-uploads its one boundary frame).
@@ -830,16 +842,7 @@ def main():
                 t[0], t[1], t[2], t[3], 1e3 * (t[5] - t[4]), 1e3 * (t[6] - t[5]), 1e3 * (t[7] - t[6]), 1e3 * (t[8] - t[7]),
                 1e3 * (t[9] - t[8]), 1e3 * (t[4] - tz), 1e3 * (t[9] - tz)))
 
-    # ---- roofline of the dominant kernel, from per-launch CUDA events in one extra profiled step
-    ctx.profile_reset()
-    ctx.profile(True)
-    ctx.timer_start()
-    step()
-    ms_prof = ctx.timer_stop()
-    ctx.profile(False)
-    kern = {k: ctx.profile_get(k) for k in ("k_icp_persist", "k_icp_step", "k_icp_stream", "k_icp_rescan", "k_icp_solve", "grid_build", "k_canny_nms",
-                                            "edge_hysteresis_compact", "k_approx_voxel", "k_transform2", "k_ndt_eval",
-                                            "ndt_voxel_build")}
+    kern = prof_snapshot
     dom = "k_icp_persist" if kern["k_icp_persist"]["launches"] else ("k_icp_stream" if kern["k_icp_stream"]["launches"] else "k_icp_step")
     ki = kern[dom]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

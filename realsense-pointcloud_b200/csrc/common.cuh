@@ -33,6 +33,10 @@ struct rspcl_ctx {
   cudaStream_t aux[RSPCL_AUX_STREAMS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[RSPCL_AUX_STREAMS] = {};
   bool persist_ready = false;
+  int persist_late = 0;   // consecutive launches with a late cluster start
+  int persist_clean = 0;  // consecutive launches without one
+  int persist_extra = 2;  // SMs the persistent-ICP planner may plan beyond (+) or below (-) the SM count; lowered when a launch
+                          // is seen to need a second wave (icp.cu)
   double cluster_weight[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};  // SMs a cluster of c CTAs occupies (occupancy query)
   // point-sharded mode (comm.cu)
   void* nccl_comm = nullptr;

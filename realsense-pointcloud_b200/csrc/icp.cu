@@ -1299,8 +1299,8 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
       ctx->persist_ready = true;
     }
     int* d_status = nullptr;
-    CU(ctx, scr.alloc(&d_status, (size_t)S));
-    CU(ctx, cudaMemsetAsync(d_status, 0, (size_t)S * sizeof(int), ctx->stream));
+    CU(ctx, scr.alloc(&d_status, (size_t)2 * S));  // [S] status, [S] cluster start times
+    CU(ctx, cudaMemsetAsync(d_status, 0, (size_t)2 * S * sizeof(int), ctx->stream));
     std::vector<int> hcnt(S);
     if (o.h_src_counts) {
       for (int s = 0; s < S; ++s) hcnt[s] = o.h_src_counts[s];
@@ -1313,8 +1313,15 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     // SMs one wave may use: clusters of 3 or more do not tile every GPC, and a mix of sizes is placed greedily, so the
     // planner charges every cluster size what the occupancy query says it takes and keeps two SMs in reserve (measured:
     // a batch planned for all 148 SMs left a few clusters waiting for a second wave, +20 % launch time)
-    double budget = ctx->sm_count - 2;
-    if (const char* e = getenv("RSPCL_PERSIST_BUDGET")) budget = atof(e) > 0 ? atof(e) : budget;  // tuning knob
+    // The occupancy query charges a cluster of 3 what it costs when the WHOLE chip runs clusters of 3 (3.2 SMs); in a mix
+    // the 2-CTA clusters fill the SMs those leave, so plans of up to ~152 "SMs" are resident on 148 (measured: 150 and 152
+    // run the 64-pair batch in 1.26 ms, 146 in 1.38, 154 in 1.51 with a second wave).  The planner therefore starts at
+    // sm_count + 2 and backs off, two SMs at a time down to sm_count - 2, whenever a launch reports a cluster that started
+    // long after the others (see the start-time feedback after the launch).
+    double budget = ctx->sm_count + ctx->persist_extra;
+    bool budget_forced = false;
+    if (const char* e = getenv("RSPCL_PERSIST_BUDGET"))
+      if (atof(e) > 0) budget = atof(e), budget_forced = true;  // tuning knob
     // Waves.  A batch that fits the chip -- or whose pairs all fit one CTA's registers, so that the hardware can simply
     // stream single-CTA clusters through the SMs -- is one wave.  A larger batch of larger pairs (e.g. 4096 frame pairs
     // of ~7 k points) is cut, in decreasing size, into waves that each fill the chip with register-resident slices.
@@ -1412,6 +1419,7 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
     pa.corr_iters = corr_iters;
     pa.n_pairs_total = S;
     pa.status = d_status;
+    pa.tstart = d_status + S;
     pa.order = d_order;
     pa.tidx = d_tidx;
     pa.tidx_rep = max_cl;
@@ -1455,11 +1463,38 @@ int icp_align_device(rspcl_ctx* ctx, const rspcl_cloud* src, const rspcl_cloud* 
         ++used;
       }
       prof.end();
-      std::vector<int> hs(S);
-      CU(ctx, small_d2h(ctx, hs.data(), d_status, (size_t)S * sizeof(int)));
+      std::vector<int> hs((size_t)2 * S);
+      CU(ctx, small_d2h(ctx, hs.data(), d_status, (size_t)2 * S * sizeof(int)));
       CU(ctx, small_d2h(ctx, hst.data(), st, (size_t)S * sizeof(IcpState)));
       if (two_stage) CU(ctx, small_d2h(ctx, hst2.data(), st2, (size_t)S * sizeof(IcpState)));
       CU(ctx, ctx_sync(ctx));
+      if (waves.size() == 1 && (int)todo.size() <= ctx->sm_count && !budget_forced && todo.size() > 1) {
+        // one-wave plan: every cluster should have started within microseconds of the first.  A cluster that started
+        // hundreds of microseconds late was waiting for SMs -- the plan was too big for this chip's GPC layout.
+        int lo = 0, hi = 0;
+        const int t0 = hs[S + todo[0]];
+        for (int s : todo) {
+          int d = (hs[S + s] - t0) & 0x7fffffff;
+          if (d > 0x3fffffff) d = d - 0x7fffffff - 1;  // (31-bit wrap)
+          lo = d < lo ? d : lo;
+          hi = d > hi ? d : hi;
+        }
+        if (hi - lo > 200) {  // ~0.2 ms; twice in a row (a single late start can be the host being slow to enqueue a group)
+          if (++ctx->persist_late >= 2 && ctx->persist_extra > -2) {
+            ctx->persist_extra -= 2;
+            ctx->persist_late = 0;
+          }
+          ctx->persist_clean = 0;
+        } else {
+          ctx->persist_late = 0;
+          // late starts also happen when another stream / context keeps SMs busy (pipelined callers): after a run of
+          // clean launches the planner tries the larger plan again
+          if (++ctx->persist_clean >= 32 && ctx->persist_extra < 2) {
+            ctx->persist_extra += 2;
+            ctx->persist_clean = 0;
+          }
+        }
+      }
       if (want_dbg) {
         std::vector<long long> hd((size_t)S * max_cl * 8);
         CU(ctx, cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));

@@ -150,6 +150,7 @@ struct PersistArgs {
   int corr_iters;           // iterations to dump (1 = PCL-style first correspondences)
   int n_pairs_total;        // pairs of the whole batch (dump layout)
   int* status;              // 1: the pair does not fit the shared-memory grid -> global-memory path
+  int* tstart;              // optional [pair]: %globaltimer >> 10 (~us) at which the pair's cluster started (wave feedback)
   const int* order;         // pairs of this launch, largest first
   unsigned short* tidx;     // scratch: original target index of every cell-sorted point, one replica per CTA of a cluster
   int tidx_rep;             // replicas per pair in tidx (>= the largest cluster of the batch)
@@ -295,6 +296,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_icp_persist(const PersistArgs 
   // correspondences, so it lives in global memory (one copy per CTA: the order inside a cell depends on each CTA's
   // atomics) and the 2 B per point it would cost in shared memory buy 2048 more resident target points
   unsigned short* TI = A.tidx + ((size_t)pair * A.tidx_rep + crank) * P_NTMAX;
+  if (A.tstart && tid == 0 && crank == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    A.tstart[pair] = (int)((gt >> 10) & 0x7fffffffull);
+  }
 
   // ---------------------------------------------------------------- build the target replica in shared memory
   if (tid == 0) {
