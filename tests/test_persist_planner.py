@@ -59,3 +59,21 @@ def test_cluster_weights_from_the_occupancy_query_are_respected():
     assert sum(w[c - 1] for c in cl) <= 146 + 1e-9
     cl_unw, _ = plan(counts, 146)
     assert cl.sum() <= cl_unw.sum()
+
+
+def test_optimistic_budget_keeps_the_bench_plan_on_the_chip():
+    """The planner starts at SMs + 2 (icp.cu): with the measured occupancy weights (clusters of 3 charged 3.2 SMs) the plan for
+    the bench sweep must still be at most 148 CTAs -- what ran resident in one wave on the B200 (1.25 ms against 1.38 ms at
+    SMs - 2); the start-time feedback covers chips where it does not."""
+    counts = np.array([4500, 4566, 4590, 4591, 4640, 4647, 4670, 4671, 4703, 4716, 4737, 4741, 4767, 4776, 4820, 4842, 5040, 5063,
+                       5123, 5132, 5163, 6211, 6234, 6240, 6245, 6250, 6348, 7267, 7352, 7376, 7426, 7449, 7708, 7767, 7834, 7857,
+                       7918, 7919, 7954, 7957, 8010, 8059, 8175, 8513, 8703, 8729, 8750, 8778, 8866, 10232, 10432, 10458, 10460,
+                       10594, 11056, 11141, 11381, 11382, 11581, 11593, 11654, 11778, 12048, 12090])
+    w = [1, 2, 148 / 46.0, 148 / 34.0, 148 / 27.0, 148 / 22.0, 148 / 18.0, 148 / 16.0]
+    cl, chunk = plan(counts, 150, w)
+    assert cl.sum() <= 148
+    assert sum(w[c - 1] for c in cl) <= 150 + 1e-9
+    worst150 = max(cost(n, c, chunk) for n, c in zip(counts, cl))
+    cl146, _ = plan(counts, 146, w)
+    worst146 = max(cost(n, c, chunk) for n, c in zip(counts, cl146))
+    assert worst150 <= worst146 and cl.sum() >= cl146.sum()
