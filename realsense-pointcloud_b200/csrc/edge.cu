@@ -159,8 +159,12 @@ __device__ __forceinline__ void canny_blur_sobel(float (*s_gray)[GW + 1], float 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ gray, int w, int h, int stride, float t_low,
-                                                   float t_high, uint8_t* __restrict__ cls, int* __restrict__ parent) {
+// FROM_PTS: the frames carry no valid gray plane (their colours were rewritten on the device): the tile takes (r + g + b) / 3
+// straight from the points instead of a separate 320 MB pass that would write the plane first.
+template <bool FROM_PTS>
+__global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ gray, const float4* __restrict__ pts, int w, int h,
+                                                   int stride, float t_low, float t_high, uint8_t* __restrict__ cls,
+                                                   int* __restrict__ parent) {
   __shared__ float s_gray[GH][GW + 1];
   __shared__ float s_blur[BH][BW + 1];
   __shared__ float s_mag[MH][MW + 1];
@@ -173,14 +177,22 @@ __global__ void __launch_bounds__(256) k_canny_nms(const uint8_t* __restrict__ g
   const int seg = blockIdx.z;
   const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const uint8_t* g = gray + (size_t)seg * stride;
+  const uint8_t* g = FROM_PTS ? nullptr : gray + (size_t)seg * stride;
   if (tid == 0) s_ncand = 0;
 
   // 1. gray tile with replicate borders (Convolution BOUNDARY_OPTION_CLAMP).  Tiles whose halo lies inside the row (all
   //    but the first / last tile column) and whose rows are 16-byte aligned take 128-bit loads: the GW = 70 bytes of a
   //    tile row sit inside six aligned 16-byte words starting 16 bytes left of the tile.
-  const bool vec_ok = (w % 16 == 0) && (stride % 16 == 0) && c0 >= 16 && c0 + TW + 16 <= w;
-  if (vec_ok) {
+  const bool vec_ok = !FROM_PTS && (w % 16 == 0) && (stride % 16 == 0) && c0 >= 16 && c0 + TW + 16 <= w;
+  if (FROM_PTS) {
+    const float4* P = pts + (size_t)seg * stride;
+    for (int k = tid; k < GH * GW; k += 256) {
+      int i = k / GW, j = k % GW;
+      int r = clampi(r0 - 3 + i, 0, h - 1), c = clampi(c0 - 3 + j, 0, w - 1);
+      const unsigned rgb = __float_as_uint(__ldg(&P[(size_t)r * w + c].w));
+      s_gray[i][j] = (float)((((rgb >> 16) & 255u) + ((rgb >> 8) & 255u) + (rgb & 255u)) / 3u);  // == k_gray_from_pts
+    }
+  } else if (vec_ok) {
     for (int k = tid; k < GH * 6; k += 256) {
       const int i = k / 6, q = k % 6;
       const int r = clampi(r0 - 3 + i, 0, h - 1);
@@ -646,8 +658,8 @@ static int edge_extract_impl(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_
   if (out_edges->n_seg != frames->n_seg) RSPCL_FAIL(ctx, RSPCL_ERR_ARG, "edge_extract: output n_seg mismatch");
   CU(ctx, cudaSetDevice(ctx->device));
   const int w = frames->width, h = frames->height, n = w * h, S = frames->n_seg, stride = frames->stride;
-  int rc = ensure_gray(ctx, const_cast<rspcl_cloud*>(frames));
-  if (rc) return rc;
+  // a stale or missing gray plane is not rebuilt: k_canny_nms<true> reads the colours of the points directly
+  const bool from_pts = !(frames->gray && frames->gray_valid);
   const size_t tot = (size_t)S * stride;
   const int nblk = div_up(n, CB);
   uint8_t *cls = nullptr, *strong = nullptr, *mask = nullptr;
@@ -664,7 +676,10 @@ static int edge_extract_impl(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_
   dim3 g1(div_up(w, TW), div_up(h, TH), S);
   {
     ProfScope prof(ctx, "k_canny_nms", (double)S * n);
-    k_canny_nms<<<g1, dim3(64, 4), 0, ctx->stream>>>(frames->gray, w, h, stride, t_low, t_high, cls, parent);
+    if (from_pts)
+      k_canny_nms<true><<<g1, dim3(64, 4), 0, ctx->stream>>>(nullptr, frames->pts, w, h, stride, t_low, t_high, cls, parent);
+    else
+      k_canny_nms<false><<<g1, dim3(64, 4), 0, ctx->stream>>>(frames->gray, nullptr, w, h, stride, t_low, t_high, cls, parent);
     LAUNCH_CHECK(ctx);
   }
   dim3 g2(blocks_per_seg(ctx, S, n, 256), S);

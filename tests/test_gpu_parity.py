@@ -135,6 +135,53 @@ def test_edge_mask_random_images(ctx, w, h):
         assert np.array_equal(got[k], f[np.flatnonzero(m.ravel())])
 
 
+def test_edge_mask_without_a_gray_plane_and_on_a_reused_handle(ctx, sweep3):
+    """ADVICE r1 (stale gray plane) and the k_canny_nms<FROM_PTS> path: a batch whose cached (r+g+b)/3 plane is stale --
+    explicitly invalidated, or because a device-side operation rewrote the colours of a handle that had been organized
+    before -- must give the masks of its CURRENT colours."""
+    fr, _ = sweep3
+    c = ctx.upload(list(fr), W, H)
+    c.invalidate_gray()
+    edges, mask = R.edge_extract(ctx, c, want_mask=True)
+    got = edges.download()
+    for k in range(len(fr)):
+        m, _ = orc.canny(fr[k], W, H)
+        assert np.array_equal(mask[k], m), "frame %d: %d mask pixels differ" % (k, (mask[k] != m).sum())
+        assert np.array_equal(got[k], orc.extract_edges(fr[k], W, H)[0])
+    # reuse: `dst` was uploaded with frame 1 (plane valid for frame 1), then overwritten on the device with frame 0
+    src0 = ctx.upload([fr[0]], W, H)
+    dst = ctx.upload([fr[1]], W, H)
+    R.edge_extract(ctx, dst)  # (uses dst's plane once, like a previous registration would have)
+    R.transform(ctx, src0, np.eye(4), out=dst)
+    _, mask2 = R.edge_extract(ctx, dst, want_mask=True)
+    m0, _ = orc.canny(fr[0], W, H)
+    assert np.array_equal(mask2[0], m0), "%d mask pixels differ (stale gray plane?)" % (mask2[0] != m0).sum()
+
+
+@pytest.mark.parametrize("w,h", [(37, 23), (130, 17), (3, 3), (64, 48)])
+def test_edge_mask_random_images_from_points(ctx, w, h):
+    rng = np.random.default_rng(w * 131 + h)
+    frames = []
+    for _ in range(2):
+        img = np.zeros((h, w), np.uint32)
+        for _ in range(14):
+            r0, c0 = rng.integers(0, h), rng.integers(0, w)
+            img[r0:r0 + rng.integers(1, h + 1), c0:c0 + rng.integers(1, w + 1)] = rng.integers(0, 256)
+        img = np.minimum(img + rng.integers(0, 6, (h, w)).astype(np.uint32), 255).astype(np.uint32)
+        cl = rand_cloud(rng, w * h)
+        # three different channels: the plane is (r + g + b) / 3 in integer arithmetic
+        cl["rgba"] = ((img << 16) | (np.minimum(img + 1, 255) << 8) | np.maximum(img, 2) - 2).ravel() | np.uint32(0xFF000000)
+        frames.append(cl)
+    c = ctx.upload(frames, w, h)
+    c.invalidate_gray()
+    _, mask = R.edge_extract(ctx, c, want_mask=True)
+    for k, f in enumerate(frames):
+        m, dbg = orc.canny(f, w, h, debug=True)
+        if dbg["near_bin_edge"]:
+            continue
+        assert np.array_equal(mask[k], m), (k, (mask[k] != m).sum())
+
+
 def test_edge_thresholds_and_pcl32_input(ctx, pair2):
     fr, _ = pair2
     c = ctx.upload([R.to_pcl32(fr[0])], W, H, layout=R.LAYOUT_PCL32)
