@@ -662,14 +662,15 @@ static int edge_extract_impl(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_
   const bool from_pts = !(frames->gray && frames->gray_valid);
   const size_t tot = (size_t)S * stride;
   const int nblk = div_up(n, CB);
+  Scratch scr(ctx);  // released on every exit path
   uint8_t *cls = nullptr, *strong = nullptr, *mask = nullptr;
   int *parent = nullptr, *blk = nullptr, *d_over = nullptr;
-  CU(ctx, scratch_alloc(ctx, &cls, tot));
-  CU(ctx, scratch_alloc(ctx, &strong, tot));
-  CU(ctx, scratch_alloc(ctx, &mask, tot));
-  CU(ctx, scratch_alloc(ctx, &parent, tot));
-  CU(ctx, scratch_alloc(ctx, &blk, (size_t)S * nblk));
-  CU(ctx, scratch_alloc(ctx, &d_over, 1));
+  CU(ctx, scr.alloc(&cls, tot));
+  CU(ctx, scr.alloc(&strong, tot));
+  CU(ctx, scr.alloc(&mask, tot));
+  CU(ctx, scr.alloc(&parent, tot));
+  CU(ctx, scr.alloc(&blk, (size_t)S * nblk));
+  CU(ctx, scr.alloc(&d_over, 1));
   CU(ctx, cudaMemsetAsync(strong, 0, tot, ctx->stream));
   CU(ctx, cudaMemsetAsync(d_over, 0, sizeof(int), ctx->stream));
 
@@ -720,12 +721,7 @@ static int edge_extract_impl(rspcl_ctx* ctx, const rspcl_cloud* frames, float t_
     CU(ctx, small_d2h(ctx, &over, d_over, sizeof(int)));
     CU(ctx, ctx_sync(ctx));
   }
-  scratch_free(ctx, cls);
-  scratch_free(ctx, strong);
-  scratch_free(ctx, mask);
-  scratch_free(ctx, parent);
-  scratch_free(ctx, blk);
-  scratch_free(ctx, d_over);
   if (over) RSPCL_FAIL(ctx, RSPCL_ERR_CAPACITY, "edge_extract: a frame produced more edge points than the output stride %d", out_edges->stride);
+  scr.ok();
   return RSPCL_OK;
 }
